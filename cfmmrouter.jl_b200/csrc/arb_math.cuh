@@ -1,0 +1,287 @@
+// arb_math.cuh -- per-pool closed-form arbitrage, fp64, device side.
+//
+// Each function names the reference lines it reproduces (paths relative to the
+// CFMMRouter.jl tree).  Every arithmetic step that the reference performs is
+// written with an explicitly rounded intrinsic (__dmul_rn, __ddiv_rn, ...) so
+// that nvcc can never contract a*b+c into an FMA: the reference (Julia) does
+// not fuse, and ProductTwoCoin / UniV3 results are therefore bit-identical to
+// an IEEE evaluation of the reference's expressions in the reference's order.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace cfmm {
+
+struct Trade {
+  double d1, d2;  // Δ[1], Δ[2]  (tendered)
+  double l1, l2;  // Λ[1], Λ[2]  (received)
+};
+
+// Julia's max(x, 0) on Float64: NaN propagates; max(-0.0, 0) == +0.0.
+__device__ __forceinline__ double jl_max0(double x) {
+  return (x != x) ? x : (x > 0.0 ? x : 0.0);
+}
+
+// Margins of the side-selection predicates.  A side is skipped only when the
+// exact-arithmetic sign of its closed form is decided by a relative margin
+// that dwarfs the few-ulp rounding error of the reference expression; ties
+// inside the margin take the full reference form, so results stay identical.
+constexpr double kProdHi = 1.0 + 0x1p-40;
+constexpr double kProdLo = 1.0 - 0x1p-40;
+constexpr double kGeoHi = 1.0 + 0x1p-30;
+constexpr double kGeoLo = 1.0 - 0x1p-30;
+constexpr double kTiny = 1e-280;  // keep predicate products in the normal range
+constexpr double kHuge = 1e280;
+
+// ---------------------------------------------------------------------------
+// ProductTwoCoin -- src/cfmms.jl:125-126 (prod_arb_δ / prod_arb_λ), :130-140
+// ---------------------------------------------------------------------------
+
+// All four closed forms exactly as written in the reference.
+__device__ __forceinline__ Trade product_full(double R1, double R2, double g,
+                                              double v1, double v2) {
+  Trade t;
+  const double k = __dmul_rn(R1, R2);               // k = R[1]*R[2]      :132
+  const double m21 = __ddiv_rn(v2, v1);             // v[2]/v[1]
+  const double m12 = __ddiv_rn(v1, v2);             // v[1]/v[2]
+  const double g21 = __dmul_rn(g, m21);             // γ*m == m*γ bitwise
+  const double g12 = __dmul_rn(g, m12);
+  // prod_arb_δ(m, r, k, γ) = max(sqrt(γ*m*k) - r, 0)/γ                  :125
+  t.d1 = __ddiv_rn(jl_max0(__dsub_rn(__dsqrt_rn(__dmul_rn(g21, k)), R1)), g);
+  t.d2 = __ddiv_rn(jl_max0(__dsub_rn(__dsqrt_rn(__dmul_rn(g12, k)), R2)), g);
+  // prod_arb_λ(m, r, k, γ) = max(r - sqrt(k/(m*γ)), 0)                  :126
+  t.l1 = jl_max0(__dsub_rn(R1, __dsqrt_rn(__ddiv_rn(k, g12))));
+  t.l2 = jl_max0(__dsub_rn(R2, __dsqrt_rn(__ddiv_rn(k, g21))));
+  return t;
+}
+
+// Same results, evaluating only the side that can be non-zero.
+//   Δ1, Λ2 > 0  <=>  γ·v2·R2 > v1·R1        (pool underprices token 1)
+//   Δ2, Λ1 > 0  <=>  γ·v1·R1 > v2·R2
+// and with γ <= 1 at most one holds.  The non-zero pair shares γ·m, so it
+// costs 3 div + 2 sqrt instead of 6 div + 4 sqrt.
+__device__ __forceinline__ Trade product_arb(double R1, double R2, double g,
+                                             double v1, double v2, bool exact) {
+  if (exact) return product_full(R1, R2, g, v1, v2);
+  const double uA = __dmul_rn(v1, R1);
+  const double uB = __dmul_rn(v2, R2);
+  const double tA = __dmul_rn(g, uB);
+  const double tB = __dmul_rn(g, uA);
+  const bool sane = (fmin(fmin(uA, uB), fmin(tA, tB)) > kTiny) &&
+                    (fmax(fmax(uA, uB), fmax(tA, tB)) < kHuge);
+  const bool zA = tA < __dmul_rn(uA, kProdLo);  // Δ1 = Λ2 = 0 for certain
+  const bool zB = tB < __dmul_rn(uB, kProdLo);  // Δ2 = Λ1 = 0 for certain
+  const bool fA = (tA > __dmul_rn(uA, kProdHi)) && zB;
+  const bool fB = (tB > __dmul_rn(uB, kProdHi)) && zA;
+  Trade t;
+  t.d1 = t.d2 = t.l1 = t.l2 = 0.0;
+  if (sane && (fA || fB)) {
+    const double ra = fA ? R1 : R2;  // reserve of the tendered token
+    const double rb = fA ? R2 : R1;  // reserve of the received token
+    const double m = fA ? __ddiv_rn(v2, v1) : __ddiv_rn(v1, v2);
+    const double k = __dmul_rn(R1, R2);
+    const double gm = __dmul_rn(g, m);
+    const double da =
+        __ddiv_rn(jl_max0(__dsub_rn(__dsqrt_rn(__dmul_rn(gm, k)), ra)), g);
+    const double lb = jl_max0(__dsub_rn(rb, __dsqrt_rn(__ddiv_rn(k, gm))));
+    if (fA) {
+      t.d1 = da;
+      t.l2 = lb;
+    } else {
+      t.d2 = da;
+      t.l1 = lb;
+    }
+    return t;
+  }
+  if (sane && zA && zB) return t;  // strictly inside the no-trade band
+  return product_full(R1, R2, g, v1, v2);
+}
+
+// ---------------------------------------------------------------------------
+// GeometricMeanTwoCoin -- src/cfmms.jl:180-181 (geom_arb_δ / geom_arb_λ), :185-196
+// ---------------------------------------------------------------------------
+
+// geom_arb_δ(m,r1,r2,η,γ) = max((γ*m*η*r1*r2^η)^(1/(η+1)) - r2, 0)/γ      :180
+__device__ __forceinline__ double geom_arb_delta(double m, double r1, double r2,
+                                                 double e, double g) {
+  const double base = __dmul_rn(
+      __dmul_rn(__dmul_rn(__dmul_rn(g, m), e), r1), pow(r2, e));
+  const double ex = __ddiv_rn(1.0, __dadd_rn(e, 1.0));
+  return __ddiv_rn(jl_max0(__dsub_rn(pow(base, ex), r2)), g);
+}
+// geom_arb_λ(m,r1,r2,η,γ) = max(r1 - ((r2*r1^(1/η))/(η*γ*m))^(η/(1+η)), 0) :181
+__device__ __forceinline__ double geom_arb_lambda(double m, double r1,
+                                                  double r2, double e,
+                                                  double g) {
+  const double base = __ddiv_rn(__dmul_rn(r2, pow(r1, __ddiv_rn(1.0, e))),
+                                __dmul_rn(__dmul_rn(e, g), m));
+  const double ex = __ddiv_rn(e, __dadd_rn(1.0, e));
+  return jl_max0(__dsub_rn(r1, pow(base, ex)));
+}
+
+__device__ __forceinline__ Trade geomean_full(double R1, double R2, double w1,
+                                              double w2, double g, double v1,
+                                              double v2) {
+  Trade t;
+  const double eta = __ddiv_rn(w1, w2);     // η = w[1]/w[2]               :188
+  const double etai = __ddiv_rn(1.0, eta);  // 1/η
+  const double m21 = __ddiv_rn(v2, v1);
+  const double m12 = __ddiv_rn(v1, v2);
+  t.d1 = geom_arb_delta(m21, R2, R1, eta, g);    // :190
+  t.d2 = geom_arb_delta(m12, R1, R2, etai, g);   // :191
+  t.l1 = geom_arb_lambda(m12, R1, R2, etai, g);  // :193
+  t.l2 = geom_arb_lambda(m21, R2, R1, eta, g);   // :194
+  return t;
+}
+
+//   Δ1, Λ2 > 0  <=>  γ·v2·w1·R2 > v1·w2·R1 ;   Δ2, Λ1 > 0  <=>  γ·v1·w2·R1 > v2·w1·R2
+// Evaluating only the live side costs 4 pow instead of 8.
+__device__ __forceinline__ Trade geomean_arb(double R1, double R2, double w1,
+                                             double w2, double g, double v1,
+                                             double v2, bool exact) {
+  if (exact) return geomean_full(R1, R2, w1, w2, g, v1, v2);
+  const double uA = __dmul_rn(__dmul_rn(v1, w2), R1);
+  const double uB = __dmul_rn(__dmul_rn(v2, w1), R2);
+  const double tA = __dmul_rn(g, uB);
+  const double tB = __dmul_rn(g, uA);
+  const double eta = __ddiv_rn(w1, w2);
+  // the margin argument needs a moderate exponent: (t/u)^(1/(η+1))
+  const bool sane = (fmin(fmin(uA, uB), fmin(tA, tB)) > kTiny) &&
+                    (fmax(fmax(uA, uB), fmax(tA, tB)) < kHuge) &&
+                    (eta > 1e-4) && (eta < 1e4);
+  const bool zA = tA < __dmul_rn(uA, kGeoLo);
+  const bool zB = tB < __dmul_rn(uB, kGeoLo);
+  const bool fA = (tA > __dmul_rn(uA, kGeoHi)) && zB;
+  const bool fB = (tB > __dmul_rn(uB, kGeoHi)) && zA;
+  Trade t;
+  t.d1 = t.d2 = t.l1 = t.l2 = 0.0;
+  if (sane && (fA || fB)) {
+    const double m = fA ? __ddiv_rn(v2, v1) : __ddiv_rn(v1, v2);
+    const double r1 = fA ? R2 : R1;
+    const double r2 = fA ? R1 : R2;
+    const double e = fA ? eta : __ddiv_rn(1.0, eta);
+    const double d = geom_arb_delta(m, r1, r2, e, g);   // Δ of r2's token
+    const double l = geom_arb_lambda(m, r1, r2, e, g);  // Λ of r1's token
+    if (fA) {
+      t.d1 = d;
+      t.l2 = l;
+    } else {
+      t.d2 = d;
+      t.l1 = l;
+    }
+    return t;
+  }
+  if (sane && zA && zB) return t;
+  return geomean_full(R1, R2, w1, w2, g, v1, v2);
+}
+
+// ---------------------------------------------------------------------------
+// UniV3 -- src/cfmms.jl:251-259, 272-289, 294-313, 321-337, 339-395
+// ---------------------------------------------------------------------------
+
+struct BoundedProduct {  // src/cfmms.jl:272-278
+  double k, alpha, beta, R1, R2;
+};
+
+// compute_at_tick, src/cfmms.jl:294-313.  idx, current_tick are 1-based;
+// lt/lq point at this pool's first tick.
+__device__ __forceinline__ BoundedProduct univ3_tick(
+    const double* __restrict__ lt, const double* __restrict__ lq, int n_ticks,
+    double current_price, int current_tick, int idx) {
+  BoundedProduct t;
+  const double k = __ldg(lq + idx - 1);
+  const double pplus = __ldg(lt + idx - 1);                    // tick_high_price :252
+  const double pminus = (idx < n_ticks) ? __ldg(lt + idx) : 0.0;  // tick_low_price :255-259
+  t.k = k;
+  t.alpha = __dsqrt_rn(__ddiv_rn(k, pplus));
+  t.beta = __dsqrt_rn(__dmul_rn(k, pminus));
+  const double p =
+      (idx > current_tick) ? pplus : (idx < current_tick) ? pminus : current_price;
+  t.R1 = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, p)), t.alpha);
+  t.R2 = __dsub_rn(__dsqrt_rn(__dmul_rn(k, p)), t.beta);
+  return t;
+}
+
+// find_arb_pos, src/cfmms.jl:321-337
+__device__ __forceinline__ void find_arb_pos(const BoundedProduct& t,
+                                             double price, double& delta,
+                                             double& lambda) {
+  const double ra = __dadd_rn(t.R1, t.alpha);
+  const double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(t.k, price)), ra);
+  if (d <= 0.0) {
+    delta = 0.0;
+    lambda = 0.0;
+    return;
+  }
+  const double dmax = __dsub_rn(__ddiv_rn(t.k, t.beta), ra);
+  if (d >= dmax) {
+    delta = dmax;
+    lambda = t.R2;
+    return;
+  }
+  delta = d;
+  lambda = __dsub_rn(__dadd_rn(t.R2, t.beta), __dsqrt_rn(__dmul_rn(price, t.k)));
+}
+
+// find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395
+__device__ __forceinline__ Trade univ3_arb(const double* __restrict__ lt,
+                                           const double* __restrict__ lq,
+                                           int n_ticks, double current_price,
+                                           int current_tick, double g,
+                                           double v1, double v2) {
+  Trade t;
+  t.d1 = t.d2 = t.l1 = t.l2 = 0.0;
+  const double p = __ddiv_rn(v1, v2);
+  const double lo = __dmul_rn(g, current_price);
+  // no-arb interval :347
+  if (lo <= p && p <= __ddiv_rn(current_price, g)) return t;
+  if (p < lo) {
+    const double price = __ddiv_rn(p, g);
+    bool initial = true;
+    double dsum = 0.0, lsum = 0.0;
+    for (int idx = current_tick; idx <= n_ticks; ++idx) {  // get_upper_pools :316
+      const BoundedProduct pool =
+          univ3_tick(lt, lq, n_ticks, current_price, current_tick, idx);
+      if (pool.k == 0.0) {
+        initial = false;
+        continue;
+      }
+      double d, l;
+      find_arb_pos(pool, price, d, l);
+      if (!initial && (d == 0.0 || l == 0.0)) break;
+      dsum = __dadd_rn(dsum, d);
+      lsum = __dadd_rn(lsum, l);
+      initial = false;
+    }
+    t.d1 = __ddiv_rn(dsum, g);
+    t.l2 = lsum;
+  } else {
+    const double price = __ddiv_rn(1.0, __dmul_rn(g, p));
+    bool initial = true;
+    double dsum = 0.0, lsum = 0.0;
+    for (int idx = current_tick; idx >= 1; --idx) {  // flip_sides.(get_lower_pools) :375
+      BoundedProduct pool =
+          univ3_tick(lt, lq, n_ticks, current_price, current_tick, idx);
+      if (pool.k == 0.0) {
+        initial = false;
+        continue;
+      }
+      double tmp = pool.alpha;
+      pool.alpha = pool.beta;
+      pool.beta = tmp;
+      tmp = pool.R1;
+      pool.R1 = pool.R2;
+      pool.R2 = tmp;
+      double d, l;
+      find_arb_pos(pool, price, d, l);
+      if (!initial && (d == 0.0 || l == 0.0)) break;
+      dsum = __dadd_rn(dsum, d);
+      lsum = __dadd_rn(lsum, l);
+      initial = false;
+    }
+    t.d2 = __ddiv_rn(dsum, g);
+    t.l1 = lsum;
+  }
+  return t;
+}
+
+}  // namespace cfmm

@@ -1,0 +1,631 @@
+// cfmm_capi.cu -- libcfmm_b200.so: C ABI (include/cfmm_b200.h) over the sm_100a
+// sweep kernels.  Host side of the drop-in boundary: pool ingest, token sort,
+// SoA upload, sweep orchestration, trade read-back, multi-GPU exchange set-up.
+//
+// There is deliberately no CPU fallback in this file: every compute entry
+// point needs a CUDA device and fails with CFMM_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cfmm_b200.h"
+#include "peer_exchange.cuh"
+#include "sweep_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// One pool type's shard: host staging until finalize, device SoA afterwards.
+struct PoolSet {
+  int64_t m = 0;
+  // host staging (insertion order)
+  std::vector<double> R, gamma, w;        // 2m, m, 2m
+  std::vector<int64_t> Ai;                // 2m, 1-based, validated
+  std::vector<int64_t> gidx;              // m, global insertion index
+  std::vector<double> cp;                 // univ3: m
+  std::vector<int64_t> tick_off;          // univ3: m+1
+  std::vector<double> lower, liq;         // univ3: CSR
+  // after finalize
+  std::vector<int64_t> order;             // sorted position -> insertion index within type
+  std::vector<int64_t> pos_of;            // lazily: insertion index -> sorted position
+  DevBuf<double2> d_R, d_w, d_outD, d_outL;
+  DevBuf<double> d_gam, d_cp, d_lower, d_liq;
+  DevBuf<int2> d_Ai, d_tick;
+  DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
+  int64_t total_ticks = 0;
+  void release() {
+    d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
+    d_gam.release(); d_cp.release(); d_lower.release(); d_liq.release();
+    d_Ai.release(); d_tick.release(); d_gidx.release();
+  }
+};
+
+}  // namespace
+
+struct cfmm_ctx {
+  int device = 0;
+  int64_t n_tokens = 0;
+  int64_t n_pools = 0;
+  bool finalized = false;
+  bool has_trades = false;
+  PoolSet sets[3];
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<double> d_nu, d_psi;  // n, n+1
+  double* h_stage = nullptr;   // pinned, n+1
+  int sm_count = 148;
+  // options
+  int exact = 0;
+  int blocks_per_sm = 0;  // 0 = occupancy-derived
+  int64_t launches = 0;
+  std::string err;
+  cfmm::PeerExchange comm;
+};
+
+namespace {
+
+int fail(cfmm_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                      \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess)                                                     \
+      return fail((ctx), CFMM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+  } while (0)
+
+int check_common(cfmm_ctx* ctx, int64_t m, const double* R, const double* gamma,
+                 const int64_t* Ai) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  if (ctx->finalized)
+    return fail(ctx, CFMM_ERR_STATE, "pools cannot be added after cfmm_finalize");
+  if (m < 0) return fail(ctx, CFMM_ERR_INVALID, "negative pool count");
+  if (m > 0 && (!gamma || !Ai || !R))
+    return fail(ctx, CFMM_ERR_INVALID, "null array argument");
+  for (int64_t i = 0; i < m; ++i) {
+    const int64_t a = Ai[2 * i], b = Ai[2 * i + 1];
+    if (a < 1 || a > ctx->n_tokens || b < 1 || b > ctx->n_tokens)
+      return fail(ctx, CFMM_ERR_INVALID,
+                  "pool %lld: token index (%lld, %lld) outside 1..%lld",
+                  (long long)i, (long long)a, (long long)b,
+                  (long long)ctx->n_tokens);
+    if (a == b)
+      return fail(ctx, CFMM_ERR_INVALID,
+                  "pool %lld: Ai[1] == Ai[2] == %lld (a two-coin pool needs two "
+                  "distinct tokens)",
+                  (long long)i, (long long)a);
+  }
+  return CFMM_OK;
+}
+
+void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
+                   const double* gamma, const int64_t* Ai) {
+  if (R) s.R.insert(s.R.end(), R, R + 2 * m);
+  s.gamma.insert(s.gamma.end(), gamma, gamma + m);
+  s.Ai.insert(s.Ai.end(), Ai, Ai + 2 * m);
+  for (int64_t i = 0; i < m; ++i) s.gidx.push_back(ctx->n_pools + i);
+  s.m += m;
+  ctx->n_pools += m;
+}
+
+// stable counting sort of pools by first token (0-based key = Ai[2i]-1)
+void token_sort(const PoolSet& s, int64_t n_tokens, std::vector<int64_t>& order) {
+  std::vector<int64_t> head((size_t)n_tokens + 1, 0);
+  for (int64_t i = 0; i < s.m; ++i) head[(size_t)s.Ai[2 * i]]++;  // key+1
+  for (int64_t t = 0; t < n_tokens; ++t) head[(size_t)t + 1] += head[(size_t)t];
+  order.assign((size_t)s.m, 0);
+  for (int64_t i = 0; i < s.m; ++i) order[(size_t)head[(size_t)s.Ai[2 * i] - 1]++] = i;
+}
+
+int upload_set(cfmm_ctx* ctx, int type) {
+  PoolSet& s = ctx->sets[type];
+  if (s.m == 0) return CFMM_OK;
+  token_sort(s, ctx->n_tokens, s.order);
+  const int64_t m = s.m;
+  std::vector<double> gam((size_t)m);
+  std::vector<int2> ai((size_t)m);
+  std::vector<int64_t> gidx((size_t)m);
+  for (int64_t p = 0; p < m; ++p) {
+    const int64_t i = s.order[(size_t)p];
+    gam[(size_t)p] = s.gamma[(size_t)i];
+    ai[(size_t)p] = make_int2((int)(s.Ai[2 * i] - 1), (int)(s.Ai[2 * i + 1] - 1));
+    gidx[(size_t)p] = s.gidx[(size_t)i];
+  }
+  CU_TRY(ctx, s.d_gam.upload(gam));
+  CU_TRY(ctx, s.d_Ai.upload(ai));
+  CU_TRY(ctx, s.d_gidx.upload(gidx));
+  if (type != CFMM_POOL_UNIV3) {
+    std::vector<double2> r((size_t)m);
+    for (int64_t p = 0; p < m; ++p) {
+      const int64_t i = s.order[(size_t)p];
+      r[(size_t)p] = make_double2(s.R[2 * i], s.R[2 * i + 1]);
+    }
+    CU_TRY(ctx, s.d_R.upload(r));
+  }
+  if (type == CFMM_POOL_GEOMEAN) {
+    std::vector<double2> w((size_t)m);
+    for (int64_t p = 0; p < m; ++p) {
+      const int64_t i = s.order[(size_t)p];
+      w[(size_t)p] = make_double2(s.w[2 * i], s.w[2 * i + 1]);
+    }
+    CU_TRY(ctx, s.d_w.upload(w));
+  }
+  if (type == CFMM_POOL_UNIV3) {
+    std::vector<double> cp((size_t)m), lower, liq;
+    std::vector<int2> tick((size_t)m);
+    lower.reserve(s.lower.size());
+    liq.reserve(s.liq.size());
+    for (int64_t p = 0; p < m; ++p) {
+      const int64_t i = s.order[(size_t)p];
+      const int64_t b = s.tick_off[(size_t)i], e = s.tick_off[(size_t)i + 1];
+      cp[(size_t)p] = s.cp[(size_t)i];
+      // current_tick = searchsortedlast(lower_ticks, current_price; rev=true)
+      // (src/cfmms.jl:235): number of leading ticks >= current_price
+      int cur = 0;
+      while (b + cur < e && s.lower[(size_t)(b + cur)] >= s.cp[(size_t)i]) ++cur;
+      tick[(size_t)p] = make_int2((int)lower.size(), cur);
+      lower.insert(lower.end(), s.lower.begin() + b, s.lower.begin() + e);
+      liq.insert(liq.end(), s.liq.begin() + b, s.liq.begin() + e);
+    }
+    s.total_ticks = (int64_t)lower.size();
+    CU_TRY(ctx, s.d_cp.upload(cp));
+    CU_TRY(ctx, s.d_tick.upload(tick));
+    CU_TRY(ctx, s.d_lower.upload(lower));
+    CU_TRY(ctx, s.d_liq.upload(liq));
+  }
+  // host staging is no longer needed (order is kept for update_reserves)
+  std::vector<double>().swap(s.R);
+  std::vector<double>().swap(s.gamma);
+  std::vector<double>().swap(s.w);
+  std::vector<int64_t>().swap(s.Ai);
+  std::vector<int64_t>().swap(s.gidx);
+  std::vector<double>().swap(s.cp);
+  std::vector<int64_t>().swap(s.tick_off);
+  std::vector<double>().swap(s.lower);
+  std::vector<double>().swap(s.liq);
+  return CFMM_OK;
+}
+
+template <class P>
+int launch_sweep(cfmm_ctx* ctx, const P& pools, PoolSet& s, const double* d_v,
+                 double* d_psi, bool mat, cudaStream_t st) {
+  constexpr int U = 2;
+  const int64_t per_block = (int64_t)cfmm::kSweepThreads * U;
+  int64_t blocks = (s.m + per_block - 1) / per_block;
+  // persistent-style grid: one wave of resident CTAs (148 SMs x occupancy)
+  static int occ_mat = 0, occ_grad = 0;
+  int& occ = mat ? occ_mat : occ_grad;
+  if (occ == 0) {
+    if (mat)
+      CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &occ, cfmm::sweep_kernel<P, true, U>, cfmm::kSweepThreads, 0));
+    else
+      CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &occ, cfmm::sweep_kernel<P, false, U>, cfmm::kSweepThreads, 0));
+    if (occ < 1) occ = 1;
+  }
+  const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
+  const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (mat) {
+    if (s.d_outD.n != (size_t)s.m) {
+      CU_TRY(ctx, s.d_outD.alloc((size_t)s.m));
+      CU_TRY(ctx, s.d_outL.alloc((size_t)s.m));
+    }
+    cfmm::sweep_kernel<P, true, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
+        pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, s.m,
+        ctx->exact);
+  } else {
+    cfmm::sweep_kernel<P, false, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
+        pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, s.m, ctx->exact);
+  }
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return CFMM_OK;
+}
+
+int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
+                  cudaStream_t st) {
+  const size_t bytes = (size_t)(ctx->n_tokens + 1) * sizeof(double);
+  CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+  CU_TRY(ctx, cudaMemsetAsync(d_psi, 0, bytes, st));
+  int rc;
+  {
+    PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
+    if (s.m > 0) {
+      cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
+      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+    }
+  }
+  {
+    PoolSet& s = ctx->sets[CFMM_POOL_GEOMEAN];
+    if (s.m > 0) {
+      cfmm::GeomeanPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_w.p};
+      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+    }
+  }
+  {
+    PoolSet& s = ctx->sets[CFMM_POOL_UNIV3];
+    if (s.m > 0) {
+      cfmm::Univ3Pools p{s.d_cp.p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
+                         s.d_lower.p, s.d_liq.p, s.m, (int)s.total_ticks};
+      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+    }
+  }
+  if (ctx->comm.attached()) {
+    if (!ctx->comm.all_reduce(d_psi, ctx->n_tokens + 1, st))
+      return fail(ctx, CFMM_ERR_COMM, "peer exchange failed: %s",
+                  ctx->comm.error().c_str());
+    ctx->launches += ctx->comm.launches_per_reduce();
+  }
+  CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+  if (mat) ctx->has_trades = true;
+  return CFMM_OK;
+}
+
+int ready(cfmm_ctx* ctx) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  if (!ctx->finalized)
+    return fail(ctx, CFMM_ERR_STATE, "cfmm_finalize has not been called");
+  return CFMM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+const char* cfmm_version(void) { return "0.1.0"; }
+
+const char* cfmm_last_error(const cfmm_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
+  if (!out) return fail(nullptr, CFMM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_tokens < 1 || n_tokens > (int64_t)0x7ffffff0)
+    return fail(nullptr, CFMM_ERR_INVALID, "n_tokens must be in 1..2^31-16");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, CFMM_ERR_CUDA,
+                "no CUDA device available (%s); libcfmm_b200 has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= n_dev)
+    return fail(nullptr, CFMM_ERR_INVALID, "device %d out of range 0..%d", device,
+                n_dev - 1);
+  cfmm_ctx* ctx = new (std::nothrow) cfmm_ctx();
+  if (!ctx) return fail(nullptr, CFMM_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->n_tokens = n_tokens;
+#define CREATE_TRY(expr)                                                    \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) {                                                \
+      fail(nullptr, CFMM_ERR_CUDA, "%s failed: %s", #expr,                  \
+           cudaGetErrorString(_e));                                         \
+      cfmm_destroy(ctx);                                                    \
+      return CFMM_ERR_CUDA;                                                 \
+    }                                                                       \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreate(&ctx->ev0));
+  CREATE_TRY(cudaEventCreate(&ctx->ev1));
+  CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
+  CREATE_TRY(ctx->d_psi.alloc((size_t)n_tokens + 1));
+  CREATE_TRY(cudaMallocHost((void**)&ctx->h_stage, (size_t)(n_tokens + 1) * sizeof(double)));
+#undef CREATE_TRY
+  *out = ctx;
+  return CFMM_OK;
+}
+
+void cfmm_destroy(cfmm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->comm.detach();
+  for (auto& s : ctx->sets) s.release();
+  ctx->d_nu.release();
+  ctx->d_psi.release();
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int cfmm_add_product(cfmm_ctx* ctx, int64_t m, const double* R,
+                     const double* gamma, const int64_t* Ai) {
+  int rc = check_common(ctx, m, R, gamma, Ai);
+  if (rc != CFMM_OK) return rc;
+  append_common(ctx, ctx->sets[CFMM_POOL_PRODUCT], m, R, gamma, Ai);
+  return CFMM_OK;
+}
+
+int cfmm_add_geomean(cfmm_ctx* ctx, int64_t m, const double* R,
+                     const double* gamma, const int64_t* Ai, const double* w) {
+  int rc = check_common(ctx, m, R, gamma, Ai);
+  if (rc != CFMM_OK) return rc;
+  if (m > 0 && !w) return fail(ctx, CFMM_ERR_INVALID, "null weight array");
+  PoolSet& s = ctx->sets[CFMM_POOL_GEOMEAN];
+  append_common(ctx, s, m, R, gamma, Ai);
+  s.w.insert(s.w.end(), w, w + 2 * m);
+  return CFMM_OK;
+}
+
+int cfmm_add_univ3(cfmm_ctx* ctx, int64_t m, const double* current_price,
+                   const double* gamma, const int64_t* Ai,
+                   const int64_t* tick_off, const double* lower_ticks,
+                   const double* liquidity) {
+  static const double dummy = 0.0;
+  int rc = check_common(ctx, m, m > 0 ? &dummy : nullptr, gamma, Ai);
+  if (rc != CFMM_OK) return rc;
+  if (m == 0) return CFMM_OK;
+  if (!current_price || !tick_off || !lower_ticks || !liquidity)
+    return fail(ctx, CFMM_ERR_INVALID, "null array argument");
+  if (tick_off[0] != 0)
+    return fail(ctx, CFMM_ERR_INVALID, "tick_off[0] must be 0");
+  PoolSet& s = ctx->sets[CFMM_POOL_UNIV3];
+  for (int64_t i = 0; i < m; ++i) {
+    const int64_t b = tick_off[i], e = tick_off[i + 1];
+    if (e <= b)
+      return fail(ctx, CFMM_ERR_INVALID, "univ3 pool %lld has no ticks", (long long)i);
+    for (int64_t t = b + 1; t < e; ++t)
+      if (!(lower_ticks[t] < lower_ticks[t - 1]))
+        return fail(ctx, CFMM_ERR_INVALID,
+                    "univ3 pool %lld: lower_ticks must be strictly decreasing",
+                    (long long)i);
+    if (!(lower_ticks[b] >= current_price[i]))
+      return fail(ctx, CFMM_ERR_INVALID,
+                  "univ3 pool %lld: current_price above the first lower tick "
+                  "(current_tick == 0; BoundsError in the reference)",
+                  (long long)i);
+  }
+  const int64_t n_ticks = tick_off[m];
+  if ((int64_t)s.lower.size() + n_ticks > (int64_t)0x7fffffff)
+    return fail(ctx, CFMM_ERR_INVALID, "more than 2^31-1 ticks in one context");
+  const int64_t base = (int64_t)s.lower.size();
+  if (s.tick_off.empty()) s.tick_off.push_back(0);
+  for (int64_t i = 1; i <= m; ++i) s.tick_off.push_back(base + tick_off[i]);
+  s.cp.insert(s.cp.end(), current_price, current_price + m);
+  s.lower.insert(s.lower.end(), lower_ticks, lower_ticks + n_ticks);
+  s.liq.insert(s.liq.end(), liquidity, liquidity + n_ticks);
+  append_common(ctx, s, m, nullptr, gamma, Ai);
+  return CFMM_OK;
+}
+
+int cfmm_finalize(cfmm_ctx* ctx) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  if (ctx->finalized) return fail(ctx, CFMM_ERR_STATE, "already finalized");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int t = 0; t < 3; ++t) {
+    int rc = upload_set(ctx, t);
+    if (rc != CFMM_OK) return rc;
+  }
+  ctx->finalized = true;
+  return CFMM_OK;
+}
+
+int64_t cfmm_num_pools(const cfmm_ctx* ctx) { return ctx ? ctx->n_pools : -1; }
+int64_t cfmm_num_tokens(const cfmm_ctx* ctx) { return ctx ? ctx->n_tokens : -1; }
+int64_t cfmm_launch_count(const cfmm_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int cfmm_sweep_device(cfmm_ctx* ctx, const double* d_v, double* d_psi_acc,
+                      int materialize, void* stream) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!d_v || !d_psi_acc) return fail(ctx, CFMM_ERR_INVALID, "null device pointer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return enqueue_sweep(ctx, d_v, d_psi_acc, materialize != 0, st);
+}
+
+int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
+               int materialize) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!v || !psi_out || !acc_out)
+    return fail(ctx, CFMM_ERR_INVALID, "null host pointer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t nb = (size_t)ctx->n_tokens * sizeof(double);
+  cudaStream_t st = ctx->stream;
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st));
+  rc = enqueue_sweep(ctx, ctx->d_nu.p, ctx->d_psi.p, materialize != 0, st);
+  if (rc != CFMM_OK) return rc;
+  CU_TRY(ctx, cudaMemcpyAsync(psi_out, ctx->d_psi.p, nb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, ctx->d_psi.p + ctx->n_tokens,
+                              sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  *acc_out = ctx->h_stage[0];
+  return CFMM_OK;
+}
+
+int cfmm_last_sweep_ms(cfmm_ctx* ctx, float* ms_out) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!ms_out) return fail(ctx, CFMM_ERR_INVALID, "ms_out is NULL");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+  CU_TRY(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+  return CFMM_OK;
+}
+
+int cfmm_get_trades(cfmm_ctx* ctx, double* Delta, double* Lambda) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!Delta || !Lambda) return fail(ctx, CFMM_ERR_INVALID, "null host pointer");
+  if (!ctx->has_trades)
+    return fail(ctx, CFMM_ERR_STATE,
+                "no materialising sweep has run (call cfmm_sweep with materialize=1)");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->n_pools == 0) return CFMM_OK;
+  DevBuf<double2> allD, allL;
+  CU_TRY(ctx, allD.alloc((size_t)ctx->n_pools));
+  cudaError_t e = allL.alloc((size_t)ctx->n_pools);
+  if (e != cudaSuccess) {
+    allD.release();
+    return fail(ctx, CFMM_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  for (auto& s : ctx->sets) {
+    if (s.m == 0) continue;
+    const int threads = 256;
+    const int64_t blocks = (s.m + threads - 1) / threads;
+    cfmm::scatter_trades_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        s.d_outD.p, s.d_outL.p, s.d_gidx.p, allD.p, allL.p, s.m);
+    ctx->launches++;
+  }
+  const size_t bytes = (size_t)ctx->n_pools * sizeof(double2);
+  cudaError_t e1 = cudaMemcpyAsync(Delta, allD.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e2 = cudaMemcpyAsync(Lambda, allL.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+  allD.release();
+  allL.release();
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(ctx, CFMM_ERR_CUDA, "trade read-back failed: %s",
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+  return CFMM_OK;
+}
+
+int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
+                         const double* R) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (type != CFMM_POOL_PRODUCT && type != CFMM_POOL_GEOMEAN)
+    return fail(ctx, CFMM_ERR_INVALID, "update_reserves: type must be PRODUCT or GEOMEAN");
+  PoolSet& s = ctx->sets[type];
+  if (first < 0 || count < 0 || first + count > s.m)
+    return fail(ctx, CFMM_ERR_INVALID, "update_reserves: range [%lld, %lld) outside 0..%lld",
+                (long long)first, (long long)(first + count), (long long)s.m);
+  if (count == 0) return CFMM_OK;
+  if (!R) return fail(ctx, CFMM_ERR_INVALID, "null reserve array");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (s.pos_of.empty()) {
+    s.pos_of.resize((size_t)s.m);
+    for (int64_t p = 0; p < s.m; ++p) s.pos_of[(size_t)s.order[(size_t)p]] = p;
+  }
+  std::vector<double2> newR((size_t)count);
+  for (int64_t j = 0; j < count; ++j)
+    newR[(size_t)j] = make_double2(R[2 * j], R[2 * j + 1]);
+  DevBuf<double2> d_new;
+  DevBuf<int64_t> d_pos;
+  CU_TRY(ctx, d_new.upload(newR));
+  cudaError_t e = d_pos.alloc((size_t)count);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(d_pos.p, s.pos_of.data() + first, (size_t)count * sizeof(int64_t),
+                   cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const int threads = 256;
+    cfmm::update_reserves_kernel<<<(unsigned)((count + threads - 1) / threads), threads, 0,
+                                   ctx->stream>>>(s.d_R.p, d_pos.p, d_new.p, count);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  d_new.release();
+  d_pos.release();
+  if (e != cudaSuccess)
+    return fail(ctx, CFMM_ERR_CUDA, "update_reserves failed: %s", cudaGetErrorString(e));
+  return CFMM_OK;
+}
+
+int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return CFMM_ERR_INVALID;
+  if (!strcmp(key, "exact")) {
+    ctx->exact = value != 0;
+  } else if (!strcmp(key, "blocks_per_sm")) {
+    if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
+    ctx->blocks_per_sm = (int)value;
+  } else {
+    return fail(ctx, CFMM_ERR_INVALID, "unknown option '%s'", key);
+  }
+  return CFMM_OK;
+}
+
+void* cfmm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void cfmm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- multi-GPU -----------------------------------------------------------------
+
+int cfmm_comm_export(cfmm_ctx* ctx, void* handle_out) {
+  if (!ctx || !handle_out) return CFMM_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  static_assert(sizeof(cfmm::PeerHandle) <= CFMM_COMM_HANDLE_BYTES, "handle size");
+  memset(handle_out, 0, CFMM_COMM_HANDLE_BYTES);
+  if (!ctx->comm.export_handle(ctx->n_tokens + 1, (cfmm::PeerHandle*)handle_out))
+    return fail(ctx, CFMM_ERR_COMM, "comm export failed: %s", ctx->comm.error().c_str());
+  return CFMM_OK;
+}
+
+int cfmm_comm_attach(cfmm_ctx* ctx, int world, int rank, const void* handles) {
+  if (!ctx || !handles) return CFMM_ERR_INVALID;
+  if (world < 1 || world > cfmm::kMaxPeers || rank < 0 || rank >= world)
+    return fail(ctx, CFMM_ERR_INVALID, "bad world/rank %d/%d", rank, world);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->comm.attach(world, rank, (const unsigned char*)handles,
+                        CFMM_COMM_HANDLE_BYTES, ctx->sm_count))
+    return fail(ctx, CFMM_ERR_COMM, "comm attach failed: %s", ctx->comm.error().c_str());
+  return CFMM_OK;
+}
+
+int cfmm_comm_detach(cfmm_ctx* ctx) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->comm.detach();
+  return CFMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+/*
+ * cfmm_b200.h -- C ABI of libcfmm_b200.so: the B200-native replacement for the
+ * dual-decomposition inner loop of CFMMRouter.jl (reference @ 5932e42).
+ *
+ * The reference has no FFI; the seam this ABI fills is INSIDE route!
+ * (src/router.jl:58-108): the three call sites of find_arb!(r, v)
+ * (router.jl:75, 93, 104, 107) and the two fold loops of the L-BFGS-B callback
+ * (acc: router.jl:79-83, gradient scatter: router.jl:98-100).  One
+ * cfmm_sweep() call = one find_arb!(r, v) over every pool + both folds.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - every function returning int returns CFMM_OK (0) or a negative
+ *    cfmm_status; nothing throws across the boundary.  The message for the
+ *    last failure is cfmm_last_error(ctx) (ctx may be NULL for failures of
+ *    cfmm_create).  Reference behaviour being replaced: Julia exceptions
+ *    (ArgumentError from the ctors, src/cfmms.jl:77-78; BoundsError on a bad
+ *    token index).
+ *  - pointer arguments are caller-owned and borrowed for the duration of the
+ *    call only; the context owns all device memory, streams and staging.
+ *  - token indices are 1-BASED int64, exactly as Julia's cfmm.Ai
+ *    (src/cfmms.jl:15, 87, 108); valid range 1..n_tokens, Ai[1] != Ai[2].
+ *  - all values are IEEE fp64 (the only eltype the reference's tests use).
+ *  - one context = one GPU = one shard of the pools.  A context is not
+ *    thread-safe; use one per Router (the reference's callback is called
+ *    synchronously from one thread, src/router.jl:105).
+ *  - the library has NO CPU fallback: without a CUDA device every compute
+ *    entry point fails with CFMM_ERR_CUDA.
+ */
+#ifndef CFMM_B200_H
+#define CFMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfmm_ctx cfmm_ctx;
+
+typedef enum cfmm_status {
+  CFMM_OK = 0,
+  CFMM_ERR_INVALID = -1, /* bad argument (ArgumentError / BoundsError analogue) */
+  CFMM_ERR_CUDA = -2,    /* CUDA runtime failure or no device */
+  CFMM_ERR_STATE = -3,   /* call order violated (e.g. sweep before finalize) */
+  CFMM_ERR_NOMEM = -4,
+  CFMM_ERR_COMM = -5     /* multi-GPU exchange set-up failure */
+} cfmm_status;
+
+typedef enum cfmm_pool_type {
+  CFMM_POOL_PRODUCT = 0, /* ProductTwoCoin,       src/cfmms.jl:101-111 */
+  CFMM_POOL_GEOMEAN = 1, /* GeometricMeanTwoCoin, src/cfmms.jl:152-165 */
+  CFMM_POOL_UNIV3 = 2    /* UniV3,                src/cfmms.jl:226-245 */
+} cfmm_pool_type;
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+/* Replaces Router(objective, cfmms, n_tokens) (src/router.jl:18-35) for the
+ * device-side state: creates an empty pool set on CUDA device `device`. */
+int cfmm_create(cfmm_ctx **out, int device, int64_t n_tokens);
+void cfmm_destroy(cfmm_ctx *ctx);
+const char *cfmm_last_error(const cfmm_ctx *ctx);
+/* "major.minor.patch" of the library */
+const char *cfmm_version(void);
+
+/* ---- pool ingest (before cfmm_finalize) ----------------------------------- */
+/* Pools are numbered in GLOBAL INSERTION ORDER across all cfmm_add_* calls;
+ * that is the order of r.cfmms / r.Δs / r.Λs on the reference side and the
+ * order cfmm_get_trades returns. */
+
+/* m x ProductTwoCoin(R, γ, idx) (src/cfmms.jl:101-111).
+ * R: [2m] pool-major (R1,R2 per pool); gamma: [m]; Ai: [2m] 1-based. */
+int cfmm_add_product(cfmm_ctx *ctx, int64_t m, const double *R,
+                     const double *gamma, const int64_t *Ai);
+
+/* m x GeometricMeanTwoCoin(R, w, γ, idx) (src/cfmms.jl:152-165). w: [2m]. */
+int cfmm_add_geomean(cfmm_ctx *ctx, int64_t m, const double *R,
+                     const double *gamma, const int64_t *Ai, const double *w);
+
+/* m x UniV3(current_price, lower_ticks, liquidity, γ, Ai) (src/cfmms.jl:226-245)
+ * in CSR form: pool i owns ticks tick_off[i] .. tick_off[i+1]-1 of
+ * lower_ticks / liquidity (tick_off: [m+1], tick_off[0] == 0); lower_ticks
+ * strictly decreasing within a pool.  current_tick is computed by the library
+ * exactly as the reference ctor does (searchsortedlast rev=true, cfmms.jl:235);
+ * a pool whose current_price exceeds its first lower tick (current_tick == 0,
+ * a BoundsError in the reference) is rejected with CFMM_ERR_INVALID. */
+int cfmm_add_univ3(cfmm_ctx *ctx, int64_t m, const double *current_price,
+                   const double *gamma, const int64_t *Ai,
+                   const int64_t *tick_off, const double *lower_ticks,
+                   const double *liquidity);
+
+/* Sort each pool type by its first token, lay it out SoA and upload. */
+int cfmm_finalize(cfmm_ctx *ctx);
+
+int64_t cfmm_num_pools(const cfmm_ctx *ctx);
+int64_t cfmm_num_tokens(const cfmm_ctx *ctx);
+
+/* ---- the hot path --------------------------------------------------------- */
+
+/* One dual-gradient sweep at price vector v (host, [n_tokens]):
+ *   find_arb!(r, v)                         src/router.jl:38-42
+ *   acc  = Σ_i dot(Λ_i, v[Ai]) - dot(Δ_i, v[Ai])      src/router.jl:79-83
+ *   psi  = Σ_i A_i (Λ_i - Δ_i)              src/router.jl:98-100 (G minus grad!(objective))
+ * psi_out: host [n_tokens]; acc_out: host scalar.  With materialize != 0 the
+ * per-pool trades Δ_i, Λ_i are also kept on the device (the final sweep of
+ * route!, router.jl:107) for cfmm_get_trades.  Blocking: results are valid on
+ * return.  When the context belongs to a multi-GPU group (cfmm_comm_attach),
+ * psi/acc are the sums over all ranks' shards and every rank must call it.
+ * Buffers from cfmm_host_alloc (pinned) avoid a staging copy. */
+int cfmm_sweep(cfmm_ctx *ctx, const double *v, double *psi_out,
+               double *acc_out, int materialize);
+
+/* Same sweep with ν already resident in device memory and the result left
+ * there: d_v [n_tokens], d_psi_acc [n_tokens + 1] = [psi ; acc], both device
+ * pointers on the context's device.  Enqueued on `stream` (a cudaStream_t;
+ * NULL = the context's own stream) WITHOUT synchronising. */
+int cfmm_sweep_device(cfmm_ctx *ctx, const double *d_v, double *d_psi_acc,
+                      int materialize, void *stream);
+
+/* Trades of the last materialising sweep, in global insertion order:
+ * Delta, Lambda: host [2 * cfmm_num_pools] pool-major (r.Δs[i], r.Λs[i]). */
+int cfmm_get_trades(cfmm_ctx *ctx, double *Delta, double *Lambda);
+
+/* Overwrite reserves of pools [first, first+count) of one type, counted in
+ * that type's own insertion order; R: [2*count].  (The reference reads
+ * cfmm.R live on every sweep, so a caller that mutates reserves between
+ * route! calls must push them.)  PRODUCT and GEOMEAN only. */
+int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
+                         const double *R);
+
+/* Tunables.  Keys: "exact" (1 = evaluate all four closed forms exactly as
+ * written in the reference for every pool; 0 = default, bit-identical fast
+ * path that evaluates only the non-zero side, falling back to the full form
+ * near ties), "threads_per_block", "blocks_per_sm". */
+int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
+
+/* Device time (ms, CUDA events on the sweep stream) of the kernels of the
+ * last cfmm_sweep / cfmm_sweep_device call; synchronises the stream. */
+int cfmm_last_sweep_ms(cfmm_ctx *ctx, float *ms_out);
+/* Number of kernel launches issued by this context so far. */
+int64_t cfmm_launch_count(const cfmm_ctx *ctx);
+
+/* ---- pinned host memory helpers ------------------------------------------- */
+void *cfmm_host_alloc(size_t bytes);
+void cfmm_host_free(void *p);
+
+/* ---- multi-GPU: one context per GPU, one process per GPU ------------------ */
+/* Pools shard across ranks (each rank adds only its shard); the only exchange
+ * is the sum of [psi ; acc] (n_tokens+1 fp64) after each sweep.  The exchange
+ * runs over NVLink peer memory: every rank exports a handle to its exchange
+ * buffer, the host side all-gathers the handles (any transport; the Python
+ * host uses torch.distributed), and each rank attaches the others'. */
+#define CFMM_COMM_HANDLE_BYTES 128
+int cfmm_comm_export(cfmm_ctx *ctx, void *handle_out /* CFMM_COMM_HANDLE_BYTES */);
+int cfmm_comm_attach(cfmm_ctx *ctx, int world, int rank,
+                     const void *handles /* world * CFMM_COMM_HANDLE_BYTES */);
+int cfmm_comm_detach(cfmm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFMM_B200_H */
