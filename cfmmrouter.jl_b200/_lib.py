@@ -47,6 +47,8 @@ SYMBOLS = {
     "cfmm_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "cfmm_last_sweep_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
     "cfmm_launch_count": (C.c_int64, [_ctx]),
+    "cfmm_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "cfmm_profile_reset": (C.c_int, [_ctx]),
     "cfmm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cfmm_host_free": (None, [C.c_void_p]),
     "cfmm_comm_export": (C.c_int, [_ctx, C.c_void_p]),

@@ -91,6 +91,12 @@ struct cfmm_ctx {
   int64_t launches = 0;
   std::string err;
   cfmm::PeerExchange comm;
+  // optional per-kernel timing (option "profile"): event pairs per launch
+  struct Prof {
+    std::vector<cudaEvent_t> ev;  // 2 per recorded launch
+    std::vector<int> type;        // pool type (3 = peer exchange)
+    size_t used = 0;              // launches recorded
+  } prof;
 };
 
 namespace {
@@ -228,9 +234,29 @@ int upload_set(cfmm_ctx* ctx, int type) {
   return CFMM_OK;
 }
 
+// profiling: bracket one launch with events on its stream
+struct ProfScope {
+  cfmm_ctx* ctx;
+  cudaStream_t st;
+  bool on;
+  ProfScope(cfmm_ctx* c, int type, cudaStream_t s) : ctx(c), st(s) {
+    on = c->prof.used < c->prof.type.size();
+    if (on) {
+      c->prof.type[c->prof.used] = type;
+      cudaEventRecord(c->prof.ev[2 * c->prof.used], st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(ctx->prof.ev[2 * ctx->prof.used + 1], st);
+      ctx->prof.used++;
+    }
+  }
+};
+
 template <class P>
-int launch_sweep(cfmm_ctx* ctx, const P& pools, PoolSet& s, const double* d_v,
-                 double* d_psi, bool mat, cudaStream_t st) {
+int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
+                 const double* d_v, double* d_psi, bool mat, cudaStream_t st) {
   constexpr int U = 2;
   const int64_t per_block = (int64_t)cfmm::kSweepThreads * U;
   int64_t blocks = (s.m + per_block - 1) / per_block;
@@ -249,11 +275,12 @@ int launch_sweep(cfmm_ctx* ctx, const P& pools, PoolSet& s, const double* d_v,
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   const int64_t cap = (int64_t)ctx->sm_count * per_sm;
   if (blocks > cap) blocks = cap;
+  if (mat && s.d_outD.n != (size_t)s.m) {
+    CU_TRY(ctx, s.d_outD.alloc((size_t)s.m));
+    CU_TRY(ctx, s.d_outL.alloc((size_t)s.m));
+  }
+  ProfScope prof(ctx, ptype, st);
   if (mat) {
-    if (s.d_outD.n != (size_t)s.m) {
-      CU_TRY(ctx, s.d_outD.alloc((size_t)s.m));
-      CU_TRY(ctx, s.d_outL.alloc((size_t)s.m));
-    }
     cfmm::sweep_kernel<P, true, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
         pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, s.m,
         ctx->exact);
@@ -274,27 +301,31 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
   int rc;
   {
     PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
+    constexpr int PT = CFMM_POOL_PRODUCT;
     if (s.m > 0) {
       cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
-      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
   {
     PoolSet& s = ctx->sets[CFMM_POOL_GEOMEAN];
+    constexpr int PT = CFMM_POOL_GEOMEAN;
     if (s.m > 0) {
       cfmm::GeomeanPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_w.p};
-      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
   {
     PoolSet& s = ctx->sets[CFMM_POOL_UNIV3];
+    constexpr int PT = CFMM_POOL_UNIV3;
     if (s.m > 0) {
       cfmm::Univ3Pools p{s.d_cp.p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
                          s.d_lower.p, s.d_liq.p, s.m, (int)s.total_ticks};
-      if ((rc = launch_sweep(ctx, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
   if (ctx->comm.attached()) {
+    ProfScope prof(ctx, 3, st);
     if (!ctx->comm.all_reduce(d_psi, ctx->n_tokens + 1, st))
       return fail(ctx, CFMM_ERR_COMM, "peer exchange failed: %s",
                   ctx->comm.error().c_str());
@@ -372,6 +403,8 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->comm.detach();
+  for (auto e : ctx->prof.ev)
+    if (e) cudaEventDestroy(e);
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_psi.release();
@@ -582,9 +615,42 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
   } else if (!strcmp(key, "blocks_per_sm")) {
     if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
     ctx->blocks_per_sm = (int)value;
+  } else if (!strcmp(key, "profile")) {
+    // value = number of kernel launches to time with CUDA events (0 = off)
+    if (value < 0 || value > (1 << 22)) return fail(ctx, CFMM_ERR_INVALID, "profile out of range");
+    cudaSetDevice(ctx->device);
+    for (auto e : ctx->prof.ev) cudaEventDestroy(e);
+    ctx->prof.ev.assign((size_t)value * 2, nullptr);
+    ctx->prof.type.assign((size_t)value, -1);
+    ctx->prof.used = 0;
+    for (auto& e : ctx->prof.ev) CU_TRY(ctx, cudaEventCreate(&e));
   } else {
     return fail(ctx, CFMM_ERR_INVALID, "unknown option '%s'", key);
   }
+  return CFMM_OK;
+}
+
+int cfmm_profile_read(cfmm_ctx* ctx, int type, double* total_ms, int64_t* launches) {
+  if (!ctx || !total_ms || !launches) return CFMM_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  double sum = 0.0;
+  int64_t cnt = 0;
+  for (size_t i = 0; i < ctx->prof.used; ++i) {
+    if (ctx->prof.type[i] != type) continue;
+    CU_TRY(ctx, cudaEventSynchronize(ctx->prof.ev[2 * i + 1]));
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->prof.ev[2 * i], ctx->prof.ev[2 * i + 1]));
+    sum += ms;
+    ++cnt;
+  }
+  *total_ms = sum;
+  *launches = cnt;
+  return CFMM_OK;
+}
+
+int cfmm_profile_reset(cfmm_ctx* ctx) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  ctx->prof.used = 0;
   return CFMM_OK;
 }
 

@@ -127,6 +127,15 @@ class DevicePools:
     def launch_count(self) -> int:
         return int(self._lib.cfmm_launch_count(self._ctx))
 
+    def profile_read(self, pool_type: int):
+        """(total_ms, launches) of the event-timed kernels of one pool type."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        self._chk(self._lib.cfmm_profile_read(self._ctx, int(pool_type), C.byref(ms), C.byref(cnt)))
+        return float(ms.value), int(cnt.value)
+
+    def profile_reset(self):
+        self._chk(self._lib.cfmm_profile_reset(self._ctx))
+
     def trades(self):
         m = self.num_pools
         D = np.zeros((m, 2))

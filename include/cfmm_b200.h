@@ -132,7 +132,8 @@ int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
 /* Tunables.  Keys: "exact" (1 = evaluate all four closed forms exactly as
  * written in the reference for every pool; 0 = default, bit-identical fast
  * path that evaluates only the non-zero side, falling back to the full form
- * near ties), "threads_per_block", "blocks_per_sm". */
+ * near ties), "blocks_per_sm" (0 = occupancy-derived), "profile" (see
+ * cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
 /* Device time (ms, CUDA events on the sweep stream) of the kernels of the
@@ -140,6 +141,15 @@ int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 int cfmm_last_sweep_ms(cfmm_ctx *ctx, float *ms_out);
 /* Number of kernel launches issued by this context so far. */
 int64_t cfmm_launch_count(const cfmm_ctx *ctx);
+
+/* Per-kernel device timing.  cfmm_set_option(ctx, "profile", N) arms CUDA-event
+ * pairs for the next N kernel launches (recorded on the launching stream,
+ * around each sweep kernel / the peer exchange).  cfmm_profile_read sums the
+ * durations recorded so far for one pool type (cfmm_pool_type, or 3 = the
+ * multi-GPU exchange kernel); it synchronises on the recorded events.
+ * cfmm_profile_reset re-arms the same N pairs. */
+int cfmm_profile_read(cfmm_ctx *ctx, int type, double *total_ms, int64_t *launches);
+int cfmm_profile_reset(cfmm_ctx *ctx);
 
 /* ---- pinned host memory helpers ------------------------------------------- */
 void *cfmm_host_alloc(size_t bytes);

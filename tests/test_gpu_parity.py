@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes over
+libcfmm_b200.so), against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE north_star): token-index scatter bit-exact; Δ, Λ, Ψ within 1e-6
+relative.  What is actually enforced here is tighter:
+  ProductTwoCoin / UniV3 : Δ, Λ BIT-EXACT per pool (both the default fast path
+                           and exact=1), because every operation is IEEE
+                           correctly rounded on both sides;
+  GeometricMeanTwoCoin   : |Δgpu−Δcpu| ≤ 1e-12·max(R)/γ (CUDA pow vs glibc pow
+                           differ in the last ulps);
+  Ψ, acc                 : ‖Ψgpu−Ψref‖∞ ≤ 1e-6‖Ψref‖∞ AND component-wise
+                           ≤ 1e-12·Σ(|Λ|+|Δ|)_j vs an extended-precision
+                           pool-order sum (atomics reorder the fp64 adds).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from cfmmrouter_b200 import synth as s
+    return s
+
+
+def make_pools(cr, n, product=None, geomean=None, univ3=None, exact=None):
+    p = cr.DevicePools(n)
+    if product is not None:
+        p.add_product(*product)
+    if geomean is not None:
+        p.add_geomean(*geomean)
+    if univ3 is not None:
+        p.add_univ3(*univ3)
+    p.finalize()
+    if exact is not None:
+        p.set_option("exact", exact)
+    return p
+
+
+def check_psi(oracle, Ai, D, L, v, n, psi, acc):
+    accx, Gx, absG = oracle.fold_compensated(Ai, D, L, v, n)
+    ref = Gx.astype(np.float64)
+    assert np.max(np.abs(psi - ref)) <= 1e-6 * max(np.max(np.abs(ref)), 1e-300)
+    assert np.all(np.abs(psi - ref) <= 1e-12 * absG + 1e-300)
+    scale = float(np.sum(absG * v))
+    assert abs(acc - float(accx)) <= 1e-12 * scale + 1e-300
+    # acc == νᵀΨ (router.jl:79-83 vs 98-100)
+    assert abs(acc - float(np.dot(v, psi))) <= 1e-11 * scale + 1e-300
+
+
+# ---------------------------------------------------------------------------
+# known-answer tests of the reference, through find_arb!(Δ, Λ, cfmm, v)
+# ---------------------------------------------------------------------------
+
+def test_reference_kats_product(cr):
+    # test/cfmms.jl:70-90
+    D, L = np.zeros(2), np.zeros(2)
+    pool = cr.ProductTwoCoin([1, 1], 1, [1, 2])
+    cr.find_arb(D, L, pool, [1.0, 1.0])
+    assert not D.any() and not L.any()
+    cr.find_arb(D, L, pool, [2.0, 2.0])
+    assert not D.any() and not L.any()
+    cr.find_arb(D, L, pool, [2.0, 1.0])
+    assert D[0] == 0 and D[1] == 0.41421356237309515
+    assert L[0] == 0.2928932188134524 and L[1] == 0
+    assert len(cr.ProductTwoCoin([1, 1], .9, [1, 2])) == 2
+    with pytest.raises(ValueError):
+        cr.ProductTwoCoin([1, 1], .9, [1])
+
+
+@pytest.mark.parametrize("gamma", [1.0, 0.997])
+def test_reference_univ3_scenarios(cr, oracle, gamma):
+    # test/cfmms.jl:117-201: the seven price scenarios, bit-exact vs the oracle
+    cp, lt, lq = 15.0, [30.0, 20, 10, 5], [1.0, 2.0, 1.5, 0.0]
+    pool = cr.UniV3(cp, lt, lq, gamma, [1, 2])
+    assert pool.current_tick == 2
+    first = [15.0, 1.0] if gamma == 1.0 else [15.0 * (1 + gamma) / 2, 1.0]
+    for v in (first, [16.0, 1.0], [14.0, 1.0], [25.0, 1.0], [7.5, 1.0], [4.0, 1.0], [35.0, 1.0]):
+        D, L = np.zeros(2), np.zeros(2)
+        cr.find_arb(D, L, pool, v)
+        Do, Lo = oracle.univ3_arb(cp, lt, lq, gamma, v)
+        assert np.array_equal(D, Do) and np.array_equal(L, Lo), (v, D, Do, L, Lo)
+
+
+def test_golden_vectors(cr):
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "closed_forms.json")) as f:
+        g = json.load(f)
+    eps = np.finfo(np.float64).eps
+    for case in g["product"]:
+        D, L = np.zeros(2), np.zeros(2)
+        cr.find_arb(D, L, cr.ProductTwoCoin(case["R"], case["gamma"], [1, 2]), case["v"])
+        scale = max(case["R"]) / min(case["gamma"], 1.0)
+        assert np.all(np.abs(D - np.array([float(s) for s in case["Delta"]])) <= 8 * eps * scale)
+        assert np.all(np.abs(L - np.array([float(s) for s in case["Lambda"]])) <= 8 * eps * scale)
+    for case in g["geomean"][:40]:
+        D, L = np.zeros(2), np.zeros(2)
+        cr.find_arb(D, L, cr.GeometricMeanTwoCoin(case["R"], case["w"], case["gamma"], [1, 2]), case["v"])
+        scale = max(case["R"]) / min(case["gamma"], 1.0)
+        assert np.all(np.abs(D - np.array([float(s) for s in case["Delta"]])) <= 256 * eps * scale)
+        assert np.all(np.abs(L - np.array([float(s) for s in case["Lambda"]])) <= 256 * eps * scale)
+
+
+# ---------------------------------------------------------------------------
+# sweep parity per pool type
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("exact", [0, 1])
+@pytest.mark.parametrize("m,n", [(1, 2), (31, 5), (64, 7), (1000, 10), (100_000, 1000), (300_007, 4099)])
+@pytest.mark.parametrize("kind", ["near", "wide", "ones"])
+def test_product_sweep_parity(cr, oracle, synth, m, n, kind, exact):
+    R, g, Ai = synth.product_pools(m, n, seed=m + n)
+    v = synth.dual_prices(n, kind)
+    p = make_pools(cr, n, product=(R, g, Ai), exact=exact)
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    assert np.array_equal(D, Do), np.argwhere(D != Do)[:5]
+    assert np.array_equal(L, Lo), np.argwhere(L != Lo)[:5]
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    # the gradient-only sweep gives the same Ψ (up to atomic ordering)
+    psi2, acc2 = p.sweep(v, materialize=False)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi2, acc2)
+    p.close()
+
+
+def test_product_ties_and_extremes(cr, oracle):
+    """Exact ties (fee-less pool at its own price), the no-trade band edge and
+    huge/tiny magnitudes: the fast path must fall back to the full form."""
+    R = np.array([[1, 1], [3, 7], [100, 100], [1e-150, 1e-150], [1e150, 1e150], [5, 9], [2, 8], [1e3, 2e3]], dtype=float)
+    g = np.array([1, 1, 1, 1, 1, 0.5, 0.997, 0.997])
+    Ai = np.array([[1, 2], [1, 2], [2, 1], [1, 2], [2, 1], [1, 2], [3, 4], [4, 3]])
+    v = np.array([7.0, 3.0, 8.0 * 0.997, 2.0])
+    for exact in (0, 1):
+        p = make_pools(cr, 4, product=(R, g, Ai), exact=exact)
+        p.sweep(v, materialize=True)
+        D, L = p.trades()
+        Do, Lo = oracle.sweep_product(R, g, Ai, v)
+        assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+        p.close()
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+@pytest.mark.parametrize("m,n", [(1, 2), (65, 9), (50_000, 500)])
+def test_geomean_sweep_parity(cr, oracle, synth, m, n, exact):
+    R, g, Ai, w = synth.geomean_pools(m, n, seed=m)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, geomean=(R, g, Ai, w), exact=exact)
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_geomean(R, g, Ai, w, v, threads=8)
+    tol = 1e-12 * (np.max(R, axis=1) / g)[:, None]
+    assert np.all(np.abs(D - Do) <= tol) and np.all(np.abs(L - Lo) <= tol)
+    assert np.all((D == 0) == (Do == 0)) and np.all((L == 0) == (Lo == 0))
+    # 1e-6 relative where the trade is non-negligible
+    big = Do > 1e-6 * np.max(R, axis=1)[:, None]
+    assert np.all(np.abs(D - Do)[big] <= 1e-6 * Do[big])
+    # fold parity against the GPU's own per-pool trades
+    check_psi(oracle, Ai, D, L, v, n, psi, acc)
+    p.close()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("m,n", [(1, 2), (100, 6), (20_000, 300)])
+def test_univ3_sweep_parity(cr, oracle, synth, m, n, ragged):
+    cp, g, Ai, off, lt, lq = synth.univ3_pools(m, n, seed=m, ragged=ragged)
+    # prices with p/cp ~ LogU(0.25, 4): 0-3 tick crossings in both directions
+    rng = np.random.default_rng(3)
+    v = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=n))
+    p = make_pools(cr, n, univ3=(cp, g, Ai, off, lt, lq))
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_univ3(cp, g, Ai, off, lt, lq, v, threads=8)
+    assert np.array_equal(D, Do), np.argwhere(D != Do)[:5]
+    assert np.array_equal(L, Lo), np.argwhere(L != Lo)[:5]
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    p.close()
+
+
+def test_mixed_types_insertion_order(cr, oracle, synth):
+    """Trades come back in global insertion order across pool types."""
+    n = 40
+    Rp, gp, Ap = synth.product_pools(300, n, seed=1)
+    Rg, gg, Ag, wg = synth.geomean_pools(200, n, seed=2)
+    cp, gu, Au, off, lt, lq = synth.univ3_pools(100, n, seed=3)
+    v = synth.dual_prices(n, "wide")
+    p = cr.DevicePools(n)
+    p.add_product(Rp[:100], gp[:100], Ap[:100])
+    p.add_geomean(Rg, gg, Ag, wg)
+    p.add_product(Rp[100:], gp[100:], Ap[100:])
+    p.add_univ3(cp, gu, Au, off, lt, lq)
+    p.finalize()
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    D1, L1 = oracle.sweep_product(Rp, gp, Ap, v)
+    D2, L2 = oracle.sweep_geomean(Rg, gg, Ag, wg, v)
+    D3, L3 = oracle.sweep_univ3(cp, gu, Au, off, lt, lq, v)
+    assert np.array_equal(D[:100], D1[:100]) and np.array_equal(D[300:500], D1[100:])
+    assert np.allclose(D[100:300], D2, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(D[500:], D3) and np.array_equal(L[500:], L3)
+    Ai = np.concatenate([Ap[:100], Ag, Ap[100:], Au])
+    check_psi(oracle, Ai, D, L, v, n, psi, acc)
+    p.close()
+
+
+# ---------------------------------------------------------------------------
+# edge cases and error behaviour of the boundary
+# ---------------------------------------------------------------------------
+
+def test_empty_pool_set(cr):
+    p = cr.DevicePools(5)
+    p.finalize()
+    psi, acc = p.sweep(np.ones(5))
+    assert not psi.any() and acc == 0.0
+    p.close()
+
+
+def test_error_codes(cr):
+    p = cr.DevicePools(3)
+    with pytest.raises(cr.CFMMError) as e:  # BoundsError analogue
+        p.add_product([[1, 1]], [1.0], [[1, 4]])
+    assert e.value.code == -1 and "outside 1..3" in e.value.message
+    with pytest.raises(cr.CFMMError):  # duplicate index
+        p.add_product([[1, 1]], [1.0], [[2, 2]])
+    with pytest.raises(cr.CFMMError) as e:  # sweep before finalize
+        p.sweep(np.ones(3))
+    assert e.value.code == -3
+    with pytest.raises(cr.CFMMError):  # current price above the first tick
+        p.add_univ3([31.0], [1.0], [[1, 2]], [0, 2], [30.0, 20.0], [1.0, 1.0])
+    with pytest.raises(cr.CFMMError):  # ticks not decreasing
+        p.add_univ3([15.0], [1.0], [[1, 2]], [0, 2], [20.0, 30.0], [1.0, 1.0])
+    p.finalize()
+    with pytest.raises(cr.CFMMError):
+        p.add_product([[1, 1]], [1.0], [[1, 2]])
+    with pytest.raises(cr.CFMMError) as e:
+        p.trades()
+    assert e.value.code == -3
+    p.close()
+
+
+def test_update_reserves(cr, oracle, synth):
+    n = 20
+    R, g, Ai = synth.product_pools(1000, n, seed=11)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, product=(R, g, Ai))
+    R2 = R.copy()
+    R2[100:400] *= 1.5
+    p.update_reserves(0, 100, R2[100:400])
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_product(R2, g, Ai, v)
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+    p.close()
+
+
+def test_nan_propagates_like_julia_max(cr, oracle):
+    # Julia's max(x, 0) propagates NaN (CUDA fmax would not)
+    R = np.array([[np.nan, 1.0], [1.0, 2.0]])
+    g = np.array([1.0, 1.0])
+    Ai = np.array([[1, 2], [2, 3]])
+    v = np.array([1.0, 2.0, 3.0])
+    p = make_pools(cr, 3, product=(R, g, Ai))
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_product(R, g, Ai, v)
+    assert np.array_equal(np.isnan(D), np.isnan(Do)) and np.isnan(D[0]).all()
+    assert np.array_equal(D[1], Do[1]) and np.array_equal(L[1], Lo[1])
+    assert np.isnan(psi[0]) and np.isnan(acc)
+    p.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE-size properties
+# ---------------------------------------------------------------------------
+
+def test_full_size_config5_10M_pools(cr, oracle, synth):
+    """configs[4] on one GPU: 10M ProductTwoCoin pools, 50k tokens.  The C
+    oracle still finishes in seconds, so this is a direct per-pool parity check
+    at full size, plus conservation properties of Ψ."""
+    m, n = 10_000_000, 50_000
+    R, g, Ai = synth.product_pools(m, n)
+    v = synth.dual_prices(n, "near")
+    p = make_pools(cr, n, product=(R, g, Ai))
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=oracle.max_threads())
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    # idempotence: a second sweep at the same ν reproduces Ψ to rounding
+    psi2, acc2 = p.sweep(v)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi2, acc2)
+    # invariant: every pool's trade keeps ϕ(R+γΔ−Λ) ≥ ϕ(R) − sqrt(eps) (test/arb.jl:11)
+    Rp = R + g[:, None] * D - L
+    assert np.all(Rp[:, 0] * Rp[:, 1] >= R[:, 0] * R[:, 1] - np.sqrt(np.finfo(float).eps))
+    p.close()
+
+
+def test_config3_mixed_1M(cr, oracle, synth):
+    """configs[2]: 500k ProductTwoCoin + 500k GeometricMeanTwoCoin, 10k tokens."""
+    n = 10_000
+    Rp, gp, Ap = synth.product_pools(500_000, n)
+    Rg, gg, Ag, wg = synth.geomean_pools(500_000, n)
+    v = synth.dual_prices(n, "near")
+    p = make_pools(cr, n, product=(Rp, gp, Ap), geomean=(Rg, gg, Ag, wg))
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    D1, L1 = oracle.sweep_product(Rp, gp, Ap, v, threads=8)
+    D2, L2 = oracle.sweep_geomean(Rg, gg, Ag, wg, v, threads=8)
+    assert np.array_equal(D[:500_000], D1) and np.array_equal(L[:500_000], L1)
+    tol = 1e-12 * (np.max(Rg, axis=1) / gg)[:, None]
+    assert np.all(np.abs(D[500_000:] - D2) <= tol) and np.all(np.abs(L[500_000:] - L2) <= tol)
+    check_psi(oracle, np.concatenate([Ap, Ag]), D, L, v, n, psi, acc)
+    p.close()
+
+
+def test_config4_univ3_500k(cr, oracle, synth):
+    """configs[3]: 500k UniV3 pools (examples/Univ3.jl shape), 5k tokens."""
+    n = 5_000
+    cp, g, Ai, off, lt, lq = synth.univ3_pools(500_000, n)
+    rng = np.random.default_rng(3)
+    v = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=n))
+    p = make_pools(cr, n, univ3=(cp, g, Ai, off, lt, lq))
+    psi, acc = p.sweep(v, materialize=True)
+    D, L = p.trades()
+    Do, Lo = oracle.sweep_univ3(cp, g, Ai, off, lt, lq, v, threads=8)
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    p.close()
+
+
+# ---------------------------------------------------------------------------
+# route! end to end (test/arb.jl, test/swap.jl)
+# ---------------------------------------------------------------------------
+
+TOL = 1e-4
+
+
+def check_primal_feasibility(cr, r, arb=True):
+    # test/arb.jl:5-23
+    flows = np.zeros_like(r.v)
+    for D, L, c in zip(r.Δs, r.Λs, r.cfmms):
+        assert np.all(D >= -TOL) and np.all(L >= -TOL)
+        assert c.phi(c.R + c.gamma * D - L) >= c.phi() - np.sqrt(np.finfo(float).eps)
+        flows[c.Ai - 1] += L - D
+    assert np.array_equal(flows, cr.netflows(r))
+    if arb:
+        assert np.all(flows >= -TOL)
+    else:
+        assert np.sum(flows >= -TOL) == 1
+
+
+def check_dual_feasibility(r):
+    # test/arb.jl:25-28
+    assert np.all(r.v >= r.objective.lower_limit() - TOL)
+    assert np.all(r.v <= r.objective.upper_limit() + TOL)
+
+
+def test_route_readme_quickstart(cr):
+    # configs[0]: README quick-start / test/arb.jl:42-58
+    # README.md:25-39
+    pools = [cr.ProductTwoCoin([1e6, 1e6], 1, [1, 2]), cr.ProductTwoCoin([1e3, 2e3], 1, [1, 2])]
+    r = cr.Router(cr.LinearNonnegative(np.ones(2)), pools, 2)
+    cr.route(r)
+    psi = cr.netflows(r)
+    # (the absolute ϕ slack of test/arb.jl:11 is only meaningful for the small
+    # pools that test uses; with R = 1e6 one ulp of ϕ is already 1e-4)
+    assert np.all(r.Δs >= -TOL) and np.all(r.Λs >= -TOL) and np.all(psi >= -TOL)
+    check_dual_feasibility(r)
+    assert abs(psi[1] - 171.40) < 0.05 and abs(psi[0]) < 1e-3
+
+
+def test_route_simple_and_random_markets(cr):
+    # test/arb.jl:42-58: pools appended after construction are ignored
+    eq, sm = cr.ProductTwoCoin([100, 100], 1, [1, 2]), cr.ProductTwoCoin([1, 2], 1, [1, 2])
+    r = cr.Router(cr.LinearNonnegative(np.ones(2)), [eq, sm], 2)
+    r.cfmms += [eq, sm]
+    cr.route(r)
+    check_primal_feasibility(cr, r)
+    check_dual_feasibility(r)
+    # test/arb.jl:60-85
+    rng = np.random.default_rng(1234)
+    pools = []
+    for _ in range(100):
+        Ai = rng.choice(np.arange(1, 11), size=2, replace=False)
+        pools.append(cr.ProductTwoCoin(1000 * rng.random(2), 1.0, Ai))
+    r = cr.Router(cr.LinearNonnegative(rng.random(10) + 1e-3), pools, 10)
+    cr.route(r)
+    check_primal_feasibility(cr, r)
+    check_dual_feasibility(r)
+
+
+def test_route_swap_markets(cr):
+    # test/swap.jl:2-46
+    eq, sm = cr.ProductTwoCoin([100, 100], 1, [1, 2]), cr.ProductTwoCoin([1, 2], 1, [1, 2])
+    r = cr.Router(cr.BasketLiquidation(1, [5.0, 0.0]), [eq, sm], 2)
+    cr.route(r)
+    check_primal_feasibility(cr, r)
+    check_dual_feasibility(r)
+    rng = np.random.default_rng(1234)
+    pools = []
+    for _ in range(100):
+        Ai = rng.choice(np.arange(1, 11), size=2, replace=False)
+        pools.append(cr.ProductTwoCoin(1000 * rng.random(2), 1.0, Ai))
+    delta_in = np.concatenate([[0.0], 100 * rng.random(9)])
+    r = cr.Router(cr.BasketLiquidation(1, delta_in), pools, 10)
+    cr.route(r)
+    check_primal_feasibility(cr, r, arb=False)
+    check_dual_feasibility(r)
