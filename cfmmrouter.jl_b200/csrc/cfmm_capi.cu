@@ -87,6 +87,7 @@ struct cfmm_ctx {
   int sm_count = 148;
   // options
   int exact = 0;
+  int debug_skip = 0;  // measurement only (tools/explore.py)
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   int64_t launches = 0;
   std::string err;
@@ -283,10 +284,11 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   if (mat) {
     cfmm::sweep_kernel<P, true, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
         pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, s.m,
-        ctx->exact);
+        ctx->exact | (ctx->debug_skip << 1));
   } else {
     cfmm::sweep_kernel<P, false, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
-        pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, s.m, ctx->exact);
+        pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, s.m,
+        ctx->exact | (ctx->debug_skip << 1));
   }
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -615,6 +617,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
   } else if (!strcmp(key, "blocks_per_sm")) {
     if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
     ctx->blocks_per_sm = (int)value;
+  } else if (!strcmp(key, "debug_skip")) {
+    ctx->debug_skip = (int)(value & 7);
   } else if (!strcmp(key, "profile")) {
     // value = number of kernel launches to time with CUDA events (0 = off)
     if (value < 0 || value > (1 << 22)) return fail(ctx, CFMM_ERR_INVALID, "profile out of range");

@@ -164,7 +164,12 @@ template <class P, bool MAT, int U>
 __global__ void __launch_bounds__(kSweepThreads)
     sweep_kernel(P pools, const double* __restrict__ nu, double* __restrict__ psi,
                  int n_tokens, double2* __restrict__ outD,
-                 double2* __restrict__ outL, int64_t m, int exact) {
+                 double2* __restrict__ outL, int64_t m, int flags) {
+  // flags: bit0 = exact (all four closed forms); bits 1-3 are measurement
+  // switches (skip the Ψ[b] RED / the Ψ[a] segmented RED / the acc fold) used
+  // only by tools/explore.py to attribute time; the product never sets them.
+  const bool exact = flags & 1;
+  const bool skip_b = flags & 2, skip_a = flags & 4, skip_acc = flags & 8;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kSweepThreads / 32) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (kSweepThreads / 32);
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      Trade t = pools.arb(pool[u], v1[u], v2[u], exact != 0);
+      Trade t = pools.arb(pool[u], v1[u], v2[u], exact);
       if (MAT && ok[u]) {
         const int64_t i = base + u * 32 + lane;
         outD[i] = make_double2(t.d1, t.d2);
@@ -204,9 +209,9 @@ __global__ void __launch_bounds__(kSweepThreads)
       }
       // dot(Λ, ν[Ai]) − dot(Δ, ν[Ai])
       const double c = (t.l1 * v1[u] + t.l2 * v2[u]) - (t.d1 * v1[u] + t.d2 * v2[u]);
-      acc += ok[u] ? c : 0.0;
-      if (f2 != 0.0) red_add(psi + ai[u].y, f2);
-      warp_segmented_red(psi, ok[u] ? ai[u].x : -1, f1, lane);
+      if (!skip_acc) acc += ok[u] ? c : 0.0;
+      if (f2 != 0.0 && !skip_b) red_add(psi + ai[u].y, f2);
+      if (!skip_a) warp_segmented_red(psi, ok[u] ? ai[u].x : -1, f1, lane);
     }
   }
 

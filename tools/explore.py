@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Measurement helper (not product code): times the sweep kernels under
+different options to attribute time (atomics / segmented reduce / acc / math
+mode / occupancy) and reports achieved algorithmic GB/s.  Run on the GPU box."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cfmmrouter_b200 as cr
+from cfmmrouter_b200 import synth
+
+
+def time_sweeps(pools, d_nu, d_psi, iters, flush=None):
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        pools.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, st)
+    torch.cuda.synchronize()
+    pools.set_option("profile", iters * 3)
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        pools.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, st)
+    torch.cuda.synchronize()
+    out = {}
+    for t in (0, 1, 2):
+        ms, cnt = pools.profile_read(t)
+        if cnt:
+            out[t] = ms / cnt * 1e3  # us
+    pools.set_option("profile", 0)
+    return out
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    res = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def run(tag, m, n, kind, nu_kind="near", iters=30, use_flush=False, **opts):
+        p = cr.DevicePools(n)
+        if kind == "product":
+            p.add_product(*synth.product_pools(m, n))
+            bpp = 32
+        elif kind == "geomean":
+            p.add_geomean(*synth.geomean_pools(m, n))
+            bpp = 48
+        else:
+            args = synth.univ3_pools(m, n)
+            p.add_univ3(*args)
+            bpp = 32 + 16 * 4
+        p.finalize()
+        for k, v in opts.items():
+            p.set_option(k, v)
+        if kind == "univ3":
+            rng = np.random.default_rng(3)
+            nu = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=n))
+        else:
+            nu = synth.dual_prices(n, nu_kind)
+        d_nu = torch.from_numpy(nu).to(dev)
+        d_psi = torch.zeros(n + 1, dtype=torch.float64, device=dev)
+        us = time_sweeps(p, d_nu, d_psi, iters, flush if use_flush else None)
+        t = list(us.values())[0]
+        row = {"tag": tag, "m": m, "n": n, "kind": kind, "nu": nu_kind, "opts": opts, "flush": use_flush,
+               "us": round(t, 2), "Gpools_s": round(m / t / 1e3, 2), "GBs": round(m * bpp / t / 1e3, 1)}
+        print(json.dumps(row), flush=True)
+        res.append(row)
+        p.close()
+
+    M, N = 10_000_000, 50_000
+    for nu in ("near", "wide", "ones"):
+        run("c5", M, N, "product", nu)
+    run("c5 exact", M, N, "product", "near", exact=1)
+    for skip, name in ((1, "no b-RED"), (2, "no a-segRED"), (4, "no acc"), (3, "no RED at all"), (7, "math+loads only")):
+        run("c5 " + name, M, N, "product", "wide", debug_skip=skip)
+    for bps in (1, 2, 3, 4):
+        run(f"c5 blocks_per_sm={bps}", M, N, "product", "wide", blocks_per_sm=bps)
+    run("c2 L2-warm", 100_000, 1_000, "product", "near", iters=200)
+    run("c2 flushed", 100_000, 1_000, "product", "near", iters=30, use_flush=True)
+    run("1M L2-warm", 1_000_000, 10_000, "product", "near", iters=100)
+    run("1M flushed", 1_000_000, 10_000, "product", "near", iters=30, use_flush=True)
+    run("geomean 500k warm", 500_000, 10_000, "geomean", "near", iters=50)
+    run("geomean 5M", 5_000_000, 10_000, "geomean", "near", iters=10)
+    run("geomean 5M exact", 5_000_000, 10_000, "geomean", "near", iters=5, exact=1)
+    run("univ3 500k warm", 500_000, 5_000, "univ3", iters=50)
+    run("univ3 500k flushed", 500_000, 5_000, "univ3", iters=20, use_flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/explore.json", "w") as f:
+        json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
