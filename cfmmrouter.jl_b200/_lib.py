@@ -49,6 +49,7 @@ SYMBOLS = {
     "cfmm_launch_count": (C.c_int64, [_ctx]),
     "cfmm_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cfmm_profile_reset": (C.c_int, [_ctx]),
+    "cfmm_selftest_inrange_math": (C.c_int, [_ctx, _dp, _dp, C.c_int64, _ip]),
     "cfmm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cfmm_host_free": (None, [C.c_void_p]),
     "cfmm_comm_export": (C.c_int, [_ctx, C.c_void_p]),

@@ -18,6 +18,7 @@
 #include "../../include/cfmm_b200.h"
 #include "peer_exchange.cuh"
 #include "sweep_kernels.cuh"
+#include "product_tma.cuh"
 
 namespace {
 
@@ -64,6 +65,8 @@ struct PoolSet {
   DevBuf<int2> d_Ai, d_tick;
   DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
   int64_t total_ticks = 0;
+  int64_t m_padded = 0;        // product: arrays padded to whole TMA tiles
+  bool in_fast_range = false;  // every R, γ in [2^-100, 2^100] and γ <= 1
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_lower.release(); d_liq.release();
@@ -88,6 +91,9 @@ struct cfmm_ctx {
   // options
   int exact = 0;
   int debug_skip = 0;  // measurement only (tools/explore.py)
+  int tma_variant = 0; // product gradient sweep: 0 = TMA kernel (default config), -1 = first-generation kernel
+  unsigned long long epoch = 0;
+  DevBuf<unsigned long long> d_bad_epoch;
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   int64_t launches = 0;
   std::string err;
@@ -157,6 +163,11 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
   ctx->n_pools += m;
 }
 
+// lcm of the tile sizes of every product_sweep_tma instantiation below
+constexpr int64_t kTilePad = 17920;
+
+inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
+
 // stable counting sort of pools by first token (0-based key = Ai[2i]-1)
 void token_sort(const PoolSet& s, int64_t n_tokens, std::vector<int64_t>& order) {
   std::vector<int64_t> head((size_t)n_tokens + 1, 0);
@@ -180,15 +191,29 @@ int upload_set(cfmm_ctx* ctx, int type) {
     ai[(size_t)p] = make_int2((int)(s.Ai[2 * i] - 1), (int)(s.Ai[2 * i + 1] - 1));
     gidx[(size_t)p] = s.gidx[(size_t)i];
   }
+  // ProductTwoCoin arrays are padded to whole TMA tiles with zero-reserve
+  // pools (Δ = Λ = 0 at any ν), keyed like the last real pool so the token
+  // order stays monotone; the padding is invisible outside the kernels.
+  s.m_padded = m;
+  if (type == CFMM_POOL_PRODUCT) {
+    s.m_padded = (m + kTilePad - 1) / kTilePad * kTilePad;
+    const int a_last = ai[(size_t)m - 1].x;
+    gam.resize((size_t)s.m_padded, 1.0);
+    ai.resize((size_t)s.m_padded, make_int2(a_last, a_last == 0 ? 1 : 0));
+  }
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
   CU_TRY(ctx, s.d_gidx.upload(gidx));
   if (type != CFMM_POOL_UNIV3) {
-    std::vector<double2> r((size_t)m);
+    std::vector<double2> r((size_t)s.m_padded, make_double2(0.0, 0.0));
+    bool ok = true;
     for (int64_t p = 0; p < m; ++p) {
       const int64_t i = s.order[(size_t)p];
       r[(size_t)p] = make_double2(s.R[2 * i], s.R[2 * i + 1]);
+      ok = ok && fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
+           fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
     }
+    s.in_fast_range = ok;
     CU_TRY(ctx, s.d_R.upload(r));
   }
   if (type == CFMM_POOL_GEOMEAN) {
@@ -295,18 +320,70 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
+template <int THREADS, int L, int S>
+int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
+                           cudaStream_t st) {
+  using Cfg = cfmm::ProductTmaCfg<THREADS, L, S>;
+  auto kern = cfmm::product_sweep_tma<THREADS, L, S>;
+  static int occ = 0;
+  if (occ == 0) {
+    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS,
+                                                              Cfg::kSmemBytes));
+    if (occ < 1)
+      return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma<%d,%d,%d> does not fit on an SM",
+                  THREADS, L, S);
+  }
+  const int n_tiles = (int)(s.m_padded / Cfg::kTile);
+  const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
+  kern<<<grid, THREADS, Cfg::kSmemBytes, st>>>(s.d_R.p, s.d_gam.p, s.d_Ai.p, n_tiles, d_v, d_psi,
+                                               (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch,
+                                               s.in_fast_range ? 1 : 0, ctx->exact);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  return CFMM_OK;
+}
+
+int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
+                       cudaStream_t st) {
+  switch (ctx->tma_variant) {
+    case 1: return launch_product_tma_cfg<256, 7, 2>(ctx, s, d_v, d_psi, st);
+    case 2: return launch_product_tma_cfg<512, 5, 2>(ctx, s, d_v, d_psi, st);
+    case 3: return launch_product_tma_cfg<256, 5, 3>(ctx, s, d_v, d_psi, st);
+    case 4: return launch_product_tma_cfg<128, 5, 4>(ctx, s, d_v, d_psi, st);
+    case 5: return launch_product_tma_cfg<128, 7, 3>(ctx, s, d_v, d_psi, st);
+    default: return launch_product_tma_cfg<256, 5, 2>(ctx, s, d_v, d_psi, st);
+  }
+}
+
 int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
                   cudaStream_t st) {
-  const size_t bytes = (size_t)(ctx->n_tokens + 1) * sizeof(double);
   CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-  CU_TRY(ctx, cudaMemsetAsync(d_psi, 0, bytes, st));
+  // zero [Ψ; acc] and validate ν for the guard-free math (one small kernel)
+  ctx->epoch++;
+  {
+    const int threads = 256;
+    const int blocks = (int)((ctx->n_tokens + 1 + threads - 1) / threads);
+    cfmm::prepare_sweep_kernel<<<blocks, threads, 0, st>>>(d_v, d_psi, (int)ctx->n_tokens,
+                                                         ctx->d_bad_epoch.p, ctx->epoch);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+  }
   int rc;
   {
     PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
     constexpr int PT = CFMM_POOL_PRODUCT;
     if (s.m > 0) {
-      cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
-      if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      if (!mat && ctx->tma_variant >= 0 && ctx->debug_skip == 0) {
+        if ((rc = launch_product_tma(ctx, s, d_v, d_psi, st)) != CFMM_OK) return rc;
+      } else {
+        cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
+        if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      }
     }
   }
   {
@@ -394,6 +471,8 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   CREATE_TRY(cudaEventCreate(&ctx->ev1));
   CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
   CREATE_TRY(ctx->d_psi.alloc((size_t)n_tokens + 1));
+  CREATE_TRY(ctx->d_bad_epoch.alloc(1));
+  CREATE_TRY(cudaMemset(ctx->d_bad_epoch.p, 0, sizeof(unsigned long long)));
   CREATE_TRY(cudaMallocHost((void**)&ctx->h_stage, (size_t)(n_tokens + 1) * sizeof(double)));
 #undef CREATE_TRY
   *out = ctx;
@@ -410,6 +489,7 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_psi.release();
+  ctx->d_bad_epoch.release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -587,8 +667,10 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
     for (int64_t p = 0; p < s.m; ++p) s.pos_of[(size_t)s.order[(size_t)p]] = p;
   }
   std::vector<double2> newR((size_t)count);
-  for (int64_t j = 0; j < count; ++j)
+  for (int64_t j = 0; j < count; ++j) {
     newR[(size_t)j] = make_double2(R[2 * j], R[2 * j + 1]);
+    if (!fast_range_ok(R[2 * j]) || !fast_range_ok(R[2 * j + 1])) s.in_fast_range = false;
+  }
   DevBuf<double2> d_new;
   DevBuf<int64_t> d_pos;
   CU_TRY(ctx, d_new.upload(newR));
@@ -617,6 +699,9 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
   } else if (!strcmp(key, "blocks_per_sm")) {
     if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
     ctx->blocks_per_sm = (int)value;
+  } else if (!strcmp(key, "tma_variant")) {
+    if (value < -1 || value > 5) return fail(ctx, CFMM_ERR_INVALID, "tma_variant out of range");
+    ctx->tma_variant = (int)value;
   } else if (!strcmp(key, "debug_skip")) {
     ctx->debug_skip = (int)(value & 7);
   } else if (!strcmp(key, "profile")) {
@@ -665,6 +750,36 @@ void* cfmm_host_alloc(size_t bytes) {
 }
 void cfmm_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+// Test hook: number of (a/b, sqrt a, sqrt b) results, over n host-provided
+// operand pairs, where the guard-free in-range recurrences differ from the IEEE
+// intrinsics.  Must be 0 for operands in [2^-100, 2^100].
+int cfmm_selftest_inrange_math(cfmm_ctx* ctx, const double* a, const double* b, int64_t n,
+                               int64_t* mismatches) {
+  if (!ctx || !a || !b || !mismatches || n < 0) return CFMM_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf<double> da, db;
+  DevBuf<unsigned long long> dm;
+  std::vector<double> ha(a, a + n), hb(b, b + n);
+  std::vector<unsigned long long> hz(1, 0);
+  CU_TRY(ctx, da.upload(ha));
+  CU_TRY(ctx, db.upload(hb));
+  CU_TRY(ctx, dm.upload(hz));
+  if (n > 0) {
+    cfmm::inrange_math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        da.p, db.p, n, dm.p);
+    ctx->launches++;
+  }
+  unsigned long long out = 0;
+  cudaError_t e = cudaMemcpyAsync(&out, dm.p, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  da.release();
+  db.release();
+  dm.release();
+  if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "selftest failed: %s", cudaGetErrorString(e));
+  *mismatches = (int64_t)out;
+  return CFMM_OK;
 }
 
 // ---- multi-GPU -----------------------------------------------------------------

@@ -133,7 +133,8 @@ int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
  * written in the reference for every pool; 0 = default, bit-identical fast
  * path that evaluates only the non-zero side, falling back to the full form
  * near ties), "blocks_per_sm" (0 = occupancy-derived), "profile" (see
- * cfmm_profile_read). */
+ * cfmm_profile_read), "tma_variant" (tile shape of the ProductTwoCoin TMA
+ * kernel; -1 = first-generation kernel). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
 /* Device time (ms, CUDA events on the sweep stream) of the kernels of the
@@ -150,6 +151,12 @@ int64_t cfmm_launch_count(const cfmm_ctx *ctx);
  * cfmm_profile_reset re-arms the same N pairs. */
 int cfmm_profile_read(cfmm_ctx *ctx, int type, double *total_ms, int64_t *launches);
 int cfmm_profile_reset(cfmm_ctx *ctx);
+
+/* Test hook: counts, over n operand pairs (host arrays), the results of the
+ * kernels' guard-free in-range division / square root that differ from IEEE
+ * a/b, sqrt(a), sqrt(b).  0 for operands in [2^-100, 2^100]. */
+int cfmm_selftest_inrange_math(cfmm_ctx *ctx, const double *a, const double *b,
+                               int64_t n, int64_t *mismatches);
 
 /* ---- pinned host memory helpers ------------------------------------------- */
 void *cfmm_host_alloc(size_t bytes);

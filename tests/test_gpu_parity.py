@@ -205,6 +205,88 @@ def test_mixed_types_insertion_order(cr, oracle, synth):
 
 
 # ---------------------------------------------------------------------------
+# second-generation ProductTwoCoin kernel (TMA-staged, guard-free in-range math)
+# ---------------------------------------------------------------------------
+
+def test_inrange_math(cr):
+    """The guard-free div / sqrt recurrences equal IEEE `/` and sqrt bit for bit
+    on operands in the validated range, including adversarial mantissas."""
+    import ctypes as C
+    rng = np.random.default_rng(12345)
+    n = 4_000_000
+    expo = rng.integers(-100, 100, size=n)
+    a = np.ldexp(1.0 + rng.random(n), expo)
+    b = np.ldexp(1.0 + rng.random(n), rng.integers(-100, 100, size=n))
+    # mantissas near 1, near 2, all-ones, powers of two, perfect squares
+    edge = np.array([1.0, 1.0 + 2**-52, 2.0 - 2**-52, 1.5, 1.0 + 2**-26, 4.0, 9.0, 0.25, 3.0, 7.0, 1e10, 1e-10])
+    a[:len(edge) ** 2] = np.repeat(edge, len(edge))
+    b[:len(edge) ** 2] = np.tile(edge, len(edge))
+    a[1000:2000] = np.ldexp(1.0 + 2.0 ** -rng.integers(1, 53, size=1000), rng.integers(-100, 100, size=1000))
+    b[1000:2000] = np.ldexp(2.0 - 2.0 ** -rng.integers(1, 52, size=1000), rng.integers(-100, 100, size=1000))
+    p = cr.DevicePools(2)
+    bad = C.c_int64(-1)
+    rc = p._lib.cfmm_selftest_inrange_math(p._ctx, a.ctypes.data_as(C.POINTER(C.c_double)),
+                                           b.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(bad))
+    assert rc == 0 and bad.value == 0, bad.value
+    p.close()
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", ["near", "wide"])
+def test_product_gradient_sweep_variants(cr, oracle, synth, variant, kind):
+    m, n = 200_003, 3_001
+    R, g, Ai = synth.product_pools(m, n, seed=variant + 10)
+    v = synth.dual_prices(n, kind)
+    p = make_pools(cr, n, product=(R, g, Ai))
+    p.set_option("tma_variant", variant)
+    psi, acc = p.sweep(v)
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    p.close()
+
+
+def test_product_fast_kernel_fallbacks(cr, oracle, synth):
+    """Inputs outside the validated range (ν or reserves), ties and γ > 1 must
+    all give the reference result through the generic path."""
+    m, n = 50_000, 500
+    R, g, Ai = synth.product_pools(m, n, seed=5)
+    v = synth.dual_prices(n, "wide")
+    for mutate in ("nu_tiny", "nu_huge", "nu_nan", "R_tiny", "gamma_gt1", "ties"):
+        R2, g2, v2 = R.copy(), g.copy(), v.copy()
+        if mutate == "nu_tiny":
+            v2[7] = 1e-200
+        elif mutate == "nu_huge":
+            v2[11] = 1e200
+        elif mutate == "nu_nan":
+            v2[13] = np.nan
+        elif mutate == "R_tiny":
+            R2[100] = [1e-180, 1e-170]
+        elif mutate == "gamma_gt1":
+            g2[5] = 1.01
+        else:
+            # pools exactly at their no-arbitrage price: R1 ν1 == R2 ν2, γ = 1
+            g2[:1000] = 1.0
+            R2[:1000, 0] = v2[Ai[:1000, 1] - 1] * 8.0
+            R2[:1000, 1] = v2[Ai[:1000, 0] - 1] * 8.0
+        p = make_pools(cr, n, product=(R2, g2, Ai))
+        psi, acc = p.sweep(v2)
+        Do, Lo = oracle.sweep_product(R2, g2, Ai, v2, threads=8)
+        if mutate == "nu_nan":
+            accx, Gx, absG = oracle.fold_compensated(Ai, Do, Lo, v2, n)
+            ref = Gx.astype(np.float64)
+            assert np.array_equal(np.isnan(psi), np.isnan(ref)) and np.isnan(acc)
+            ok = ~np.isnan(ref)
+            assert np.all(np.abs(psi[ok] - ref[ok]) <= 1e-12 * absG[ok] + 1e-300)
+        else:
+            check_psi(oracle, Ai, Do, Lo, v2, n, psi, acc)
+        # and the materialised trades are bit-exact as always
+        p.sweep(v2, materialize=True)
+        D, L = p.trades()
+        assert np.array_equal(D, Do, equal_nan=True) and np.array_equal(L, Lo, equal_nan=True)
+        p.close()
+
+
+# ---------------------------------------------------------------------------
 # edge cases and error behaviour of the boundary
 # ---------------------------------------------------------------------------
 

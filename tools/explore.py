@@ -71,7 +71,16 @@ def main():
 
     M, N = 10_000_000, 50_000
     for nu in ("near", "wide", "ones"):
-        run("c5", M, N, "product", nu)
+        run("c5 tma", M, N, "product", nu)
+    for var in (1, 2, 3, 4, 5):
+        run(f"c5 tma_variant={var}", M, N, "product", "near", tma_variant=var)
+    for bps in (1,):
+        run(f"c5 tma blocks_per_sm={bps}", M, N, "product", "near", blocks_per_sm=bps)
+    run("c5 tma exact(generic in tma kernel)", M, N, "product", "near", exact=1)
+    run("c5 gen1", M, N, "product", "near", tma_variant=-1)
+    run("c2 tma L2-warm", 100_000, 1_000, "product", "near", iters=200)
+    run("1M tma L2-warm", 1_000_000, 10_000, "product", "near", iters=100)
+    return
     run("c5 exact", M, N, "product", "near", exact=1)
     for skip, name in ((1, "no b-RED"), (2, "no a-segRED"), (4, "no acc"), (3, "no RED at all"), (7, "math+loads only")):
         run("c5 " + name, M, N, "product", "wide", debug_skip=skip)
