@@ -29,8 +29,17 @@ constexpr double kProdHi = 1.0 + 0x1p-40;
 constexpr double kProdLo = 1.0 - 0x1p-40;
 constexpr double kGeoHi = 1.0 + 0x1p-30;
 constexpr double kGeoLo = 1.0 - 0x1p-30;
-constexpr double kTiny = 1e-280;  // keep predicate products in the normal range
-constexpr double kHuge = 1e280;
+// The side-selection certificates (and the guard-free div/sqrt of
+// product_tma.cuh) assume that no intermediate of the reference expression
+// underflows or overflows.  With every input in [2^-100, 2^101) all products,
+// quotients and roots of the ProductTwoCoin forms stay within 2^±510.
+__device__ __forceinline__ bool in_fast_range(double v) {
+  return (unsigned)(__double2hiint(v) - 0x39B00000) < (0x46400000u - 0x39B00000u);
+}
+// tighter window for the GeometricMean forms (powers up to r^24): [2^-32, 2^32)
+__device__ __forceinline__ bool in_geo_range(double v) {
+  return (unsigned)(__double2hiint(v) - 0x3DF00000) < (0x41F00000u - 0x3DF00000u);
+}
 
 // ---------------------------------------------------------------------------
 // ProductTwoCoin -- src/cfmms.jl:125-126 (prod_arb_δ / prod_arb_λ), :130-140
@@ -66,8 +75,8 @@ __device__ __forceinline__ Trade product_arb(double R1, double R2, double g,
   const double uB = __dmul_rn(v2, R2);
   const double tA = __dmul_rn(g, uB);
   const double tB = __dmul_rn(g, uA);
-  const bool sane = (fmin(fmin(uA, uB), fmin(tA, tB)) > kTiny) &&
-                    (fmax(fmax(uA, uB), fmax(tA, tB)) < kHuge);
+  const bool sane = in_fast_range(R1) && in_fast_range(R2) && in_fast_range(g) &&
+                    in_fast_range(v1) && in_fast_range(v2);
   const bool zA = tA < __dmul_rn(uA, kProdLo);  // Δ1 = Λ2 = 0 for certain
   const bool zB = tB < __dmul_rn(uB, kProdLo);  // Δ2 = Λ1 = 0 for certain
   const bool fA = (tA > __dmul_rn(uA, kProdHi)) && zB;
@@ -144,10 +153,10 @@ __device__ __forceinline__ Trade geomean_arb(double R1, double R2, double w1,
   const double tA = __dmul_rn(g, uB);
   const double tB = __dmul_rn(g, uA);
   const double eta = __ddiv_rn(w1, w2);
-  // the margin argument needs a moderate exponent: (t/u)^(1/(η+1))
-  const bool sane = (fmin(fmin(uA, uB), fmin(tA, tB)) > kTiny) &&
-                    (fmax(fmax(uA, uB), fmax(tA, tB)) < kHuge) &&
-                    (eta > 1e-4) && (eta < 1e4);
+  // the margin argument needs a moderate exponent, (t/u)^(1/(η+1)), and no
+  // overflow/underflow inside the powers: inputs in [2^-32, 2^32), η in [1/24, 24]
+  const bool sane = in_geo_range(R1) && in_geo_range(R2) && in_geo_range(v1) &&
+                    in_geo_range(v2) && in_geo_range(g) && (eta > 1.0 / 24.0) && (eta < 24.0);
   const bool zA = tA < __dmul_rn(uA, kGeoLo);
   const bool zB = tB < __dmul_rn(uB, kGeoLo);
   const bool fA = (tA > __dmul_rn(uA, kGeoHi)) && zB;

@@ -65,12 +65,16 @@ struct PoolSet {
   DevBuf<int2> d_Ai, d_tick;
   DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
   int64_t total_ticks = 0;
-  int64_t m_padded = 0;        // product: arrays padded to whole TMA tiles
+  int64_t m_padded = 0;        // product: arrays padded to whole TMA tiles, per b-bucket
   bool in_fast_range = false;  // every R, γ in [2^-100, 2^100] and γ <= 1
+  bool tma_ok = false;         // b-bucketed layout built (product only)
+  int tma_variant = 0;         // tile shape the layout was built for
+  int nb = 0;                  // bucket width in tokens
+  DevBuf<int> d_tile_bucket;   // bucket of every tile
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_lower.release(); d_liq.release();
-    d_Ai.release(); d_tick.release(); d_gidx.release();
+    d_Ai.release(); d_tick.release(); d_gidx.release(); d_tile_bucket.release();
   }
 };
 
@@ -91,7 +95,8 @@ struct cfmm_ctx {
   // options
   int exact = 0;
   int debug_skip = 0;  // measurement only (tools/explore.py)
-  int tma_variant = 0; // product gradient sweep: 0 = TMA kernel (default config), -1 = first-generation kernel
+  int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
+  int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
   unsigned long long epoch = 0;
   DevBuf<unsigned long long> d_bad_epoch;
   int blocks_per_sm = 0;  // 0 = occupancy-derived
@@ -163,8 +168,19 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
   ctx->n_pools += m;
 }
 
-// lcm of the tile sizes of every product_sweep_tma instantiation below
-constexpr int64_t kTilePad = 17920;
+// product_sweep_tma instantiations: {THREADS, L, S, NBMAX, MINB}
+struct TmaVariant {
+  int threads, L, S, nbmax, minb;
+};
+constexpr TmaVariant kTmaVariants[] = {
+    {256, 3, 2, 3200, 2},  // 0 (default): 98 KB smem, 2 CTAs/SM
+    {256, 5, 2, 2048, 2},  // 1: 112 KB, 2 CTAs/SM
+    {384, 3, 2, 2048, 2},  // 2: 104 KB, 2 CTAs/SM, 24 warps
+    {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
+    {256, 3, 2, 1600, 3},  // 4: 73 KB, 3 CTAs/SM, 24 warps
+    {256, 5, 2, 3200, 1},  // 5: 130 KB, 1 CTA/SM
+};
+constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
 inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
 
@@ -182,33 +198,69 @@ int upload_set(cfmm_ctx* ctx, int type) {
   if (s.m == 0) return CFMM_OK;
   token_sort(s, ctx->n_tokens, s.order);
   const int64_t m = s.m;
-  std::vector<double> gam((size_t)m);
-  std::vector<int2> ai((size_t)m);
-  std::vector<int64_t> gidx((size_t)m);
-  for (int64_t p = 0; p < m; ++p) {
-    const int64_t i = s.order[(size_t)p];
-    gam[(size_t)p] = s.gamma[(size_t)i];
-    ai[(size_t)p] = make_int2((int)(s.Ai[2 * i] - 1), (int)(s.Ai[2 * i + 1] - 1));
-    gidx[(size_t)p] = s.gidx[(size_t)i];
-  }
-  // ProductTwoCoin arrays are padded to whole TMA tiles with zero-reserve
-  // pools (Δ = Λ = 0 at any ν), keyed like the last real pool so the token
-  // order stays monotone; the padding is invisible outside the kernels.
   s.m_padded = m;
-  if (type == CFMM_POOL_PRODUCT) {
-    s.m_padded = (m + kTilePad - 1) / kTilePad * kTilePad;
-    const int a_last = ai[(size_t)m - 1].x;
-    gam.resize((size_t)s.m_padded, 1.0);
-    ai.resize((size_t)s.m_padded, make_int2(a_last, a_last == 0 ? 1 : 0));
+  s.tma_ok = false;
+  std::vector<int> tile_bucket;
+  if (type == CFMM_POOL_PRODUCT && ctx->tma_variant >= 0) {
+    // b-bucketed order for the TMA kernel: (bucket(b), a), each bucket padded
+    // to whole tiles with zero-reserve pools (Δ = Λ = 0 at any ν).
+    const TmaVariant& tv = kTmaVariants[ctx->tma_variant];
+    const int64_t tile = (int64_t)tv.threads * tv.L;
+    const int64_t n = ctx->n_tokens;
+    const int64_t B = (n + tv.nbmax - 1) / tv.nbmax;
+    const int64_t nb = (n + B - 1) / B;
+    std::vector<int64_t> cnt((size_t)B + 1, 0);
+    for (int64_t i = 0; i < m; ++i) cnt[(size_t)((s.Ai[2 * i + 1] - 1) / nb) + 1]++;
+    int64_t padded = 0;
+    for (int64_t k = 0; k < B; ++k) padded += (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
+    if (padded <= 2 * m + 8 * tile) {  // otherwise too sparse per bucket: first-generation kernel
+      std::vector<int64_t> start((size_t)B + 1, 0);  // padded start of each bucket
+      for (int64_t k = 0; k < B; ++k)
+        start[(size_t)k + 1] = start[(size_t)k] + (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
+      std::vector<int64_t> order((size_t)padded, -1), fill(start.begin(), start.end() - 1);
+      for (int64_t p = 0; p < m; ++p) {  // stable: keeps the a-order inside a bucket
+        const int64_t i = s.order[(size_t)p];
+        order[(size_t)fill[(size_t)((s.Ai[2 * i + 1] - 1) / nb)]++] = i;
+      }
+      s.order.swap(order);
+      s.m_padded = padded;
+      s.tma_ok = true;
+      s.tma_variant = ctx->tma_variant;
+      s.nb = (int)nb;
+      tile_bucket.resize((size_t)(padded / tile));
+      for (int64_t k = 0; k < B; ++k)
+        for (int64_t t = start[(size_t)k] / tile; t < start[(size_t)k + 1] / tile; ++t)
+          tile_bucket[(size_t)t] = (int)k;
+    }
+  }
+  const int64_t mp = s.m_padded;
+  std::vector<double> gam((size_t)mp, 1.0);
+  std::vector<int2> ai((size_t)mp);
+  std::vector<int64_t> gidx((size_t)mp, -1);
+  int2 last = make_int2(0, 1);
+  for (int64_t p = 0; p < mp; ++p) {
+    const int64_t i = s.order[(size_t)p];
+    if (i < 0) {
+      // padding: keyed like the previous real pool of the bucket (monotone a);
+      // a leading pad of an empty-fronted bucket cannot occur (pads trail)
+      ai[(size_t)p] = last;
+      continue;
+    }
+    gam[(size_t)p] = s.gamma[(size_t)i];
+    last = make_int2((int)(s.Ai[2 * i] - 1), (int)(s.Ai[2 * i + 1] - 1));
+    ai[(size_t)p] = last;
+    gidx[(size_t)p] = s.gidx[(size_t)i];
   }
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
   CU_TRY(ctx, s.d_gidx.upload(gidx));
+  if (s.tma_ok) CU_TRY(ctx, s.d_tile_bucket.upload(tile_bucket));
   if (type != CFMM_POOL_UNIV3) {
-    std::vector<double2> r((size_t)s.m_padded, make_double2(0.0, 0.0));
+    std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
     bool ok = true;
-    for (int64_t p = 0; p < m; ++p) {
+    for (int64_t p = 0; p < mp; ++p) {
       const int64_t i = s.order[(size_t)p];
+      if (i < 0) continue;
       r[(size_t)p] = make_double2(s.R[2 * i], s.R[2 * i + 1]);
       ok = ok && fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
            fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
@@ -285,7 +337,8 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
                  const double* d_v, double* d_psi, bool mat, cudaStream_t st) {
   constexpr int U = 2;
   const int64_t per_block = (int64_t)cfmm::kSweepThreads * U;
-  int64_t blocks = (s.m + per_block - 1) / per_block;
+  const int64_t m_all = s.m_padded;  // includes the zero-trade padding pools, if any
+  int64_t blocks = (m_all + per_block - 1) / per_block;
   // persistent-style grid: one wave of resident CTAs (148 SMs x occupancy)
   static int occ_mat = 0, occ_grad = 0;
   int& occ = mat ? occ_mat : occ_grad;
@@ -301,18 +354,18 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   const int64_t cap = (int64_t)ctx->sm_count * per_sm;
   if (blocks > cap) blocks = cap;
-  if (mat && s.d_outD.n != (size_t)s.m) {
-    CU_TRY(ctx, s.d_outD.alloc((size_t)s.m));
-    CU_TRY(ctx, s.d_outL.alloc((size_t)s.m));
+  if (mat && s.d_outD.n != (size_t)m_all) {
+    CU_TRY(ctx, s.d_outD.alloc((size_t)m_all));
+    CU_TRY(ctx, s.d_outL.alloc((size_t)m_all));
   }
   ProfScope prof(ctx, ptype, st);
   if (mat) {
     cfmm::sweep_kernel<P, true, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
-        pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, s.m,
+        pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, m_all,
         ctx->exact | (ctx->debug_skip << 1));
   } else {
     cfmm::sweep_kernel<P, false, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
-        pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, s.m,
+        pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, m_all,
         ctx->exact | (ctx->debug_skip << 1));
   }
   ctx->launches++;
@@ -320,29 +373,29 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
-template <int THREADS, int L, int S>
+template <int V>
 int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                            cudaStream_t st) {
-  using Cfg = cfmm::ProductTmaCfg<THREADS, L, S>;
-  auto kern = cfmm::product_sweep_tma<THREADS, L, S>;
+  constexpr TmaVariant tv = kTmaVariants[V];
+  using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb>;
   static int occ = 0;
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS,
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tv.threads,
                                                               Cfg::kSmemBytes));
     if (occ < 1)
-      return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma<%d,%d,%d> does not fit on an SM",
-                  THREADS, L, S);
+      return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma variant %d does not fit on an SM", V);
   }
   const int n_tiles = (int)(s.m_padded / Cfg::kTile);
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
   if (grid > n_tiles) grid = n_tiles;
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
-  kern<<<grid, THREADS, Cfg::kSmemBytes, st>>>(s.d_R.p, s.d_gam.p, s.d_Ai.p, n_tiles, d_v, d_psi,
-                                               (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch,
-                                               s.in_fast_range ? 1 : 0, ctx->exact);
+  kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
+      s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
+      (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch, s.in_fast_range ? 1 : 0, ctx->exact);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;
@@ -350,13 +403,13 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
 
 int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                        cudaStream_t st) {
-  switch (ctx->tma_variant) {
-    case 1: return launch_product_tma_cfg<256, 7, 2>(ctx, s, d_v, d_psi, st);
-    case 2: return launch_product_tma_cfg<512, 5, 2>(ctx, s, d_v, d_psi, st);
-    case 3: return launch_product_tma_cfg<256, 5, 3>(ctx, s, d_v, d_psi, st);
-    case 4: return launch_product_tma_cfg<128, 5, 4>(ctx, s, d_v, d_psi, st);
-    case 5: return launch_product_tma_cfg<128, 7, 3>(ctx, s, d_v, d_psi, st);
-    default: return launch_product_tma_cfg<256, 5, 2>(ctx, s, d_v, d_psi, st);
+  switch (s.tma_variant) {
+    case 1: return launch_product_tma_cfg<1>(ctx, s, d_v, d_psi, st);
+    case 2: return launch_product_tma_cfg<2>(ctx, s, d_v, d_psi, st);
+    case 3: return launch_product_tma_cfg<3>(ctx, s, d_v, d_psi, st);
+    case 4: return launch_product_tma_cfg<4>(ctx, s, d_v, d_psi, st);
+    case 5: return launch_product_tma_cfg<5>(ctx, s, d_v, d_psi, st);
+    default: return launch_product_tma_cfg<0>(ctx, s, d_v, d_psi, st);
   }
 }
 
@@ -378,7 +431,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
     PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
     constexpr int PT = CFMM_POOL_PRODUCT;
     if (s.m > 0) {
-      if (!mat && ctx->tma_variant >= 0 && ctx->debug_skip == 0) {
+      if (!mat && s.tma_ok && ctx->use_tma && ctx->debug_skip == 0) {
         if ((rc = launch_product_tma(ctx, s, d_v, d_psi, st)) != CFMM_OK) return rc;
       } else {
         cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
@@ -399,7 +452,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
     constexpr int PT = CFMM_POOL_UNIV3;
     if (s.m > 0) {
       cfmm::Univ3Pools p{s.d_cp.p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
-                         s.d_lower.p, s.d_liq.p, s.m, (int)s.total_ticks};
+                         s.d_lower.p, s.d_liq.p, s.m_padded, (int)s.total_ticks};
       if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
@@ -632,9 +685,9 @@ int cfmm_get_trades(cfmm_ctx* ctx, double* Delta, double* Lambda) {
   for (auto& s : ctx->sets) {
     if (s.m == 0) continue;
     const int threads = 256;
-    const int64_t blocks = (s.m + threads - 1) / threads;
+    const int64_t blocks = (s.m_padded + threads - 1) / threads;
     cfmm::scatter_trades_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        s.d_outD.p, s.d_outL.p, s.d_gidx.p, allD.p, allL.p, s.m);
+        s.d_outD.p, s.d_outL.p, s.d_gidx.p, allD.p, allL.p, s.m_padded);
     ctx->launches++;
   }
   const size_t bytes = (size_t)ctx->n_pools * sizeof(double2);
@@ -664,7 +717,8 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (s.pos_of.empty()) {
     s.pos_of.resize((size_t)s.m);
-    for (int64_t p = 0; p < s.m; ++p) s.pos_of[(size_t)s.order[(size_t)p]] = p;
+    for (int64_t p = 0; p < s.m_padded; ++p)
+      if (s.order[(size_t)p] >= 0) s.pos_of[(size_t)s.order[(size_t)p]] = p;
   }
   std::vector<double2> newR((size_t)count);
   for (int64_t j = 0; j < count; ++j) {
@@ -700,8 +754,12 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
     ctx->blocks_per_sm = (int)value;
   } else if (!strcmp(key, "tma_variant")) {
-    if (value < -1 || value > 5) return fail(ctx, CFMM_ERR_INVALID, "tma_variant out of range");
+    if (value < -1 || value >= kNumTmaVariants) return fail(ctx, CFMM_ERR_INVALID, "tma_variant out of range");
+    if (ctx->finalized)
+      return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "use_tma")) {
+    ctx->use_tma = value != 0;
   } else if (!strcmp(key, "debug_skip")) {
     ctx->debug_skip = (int)(value & 7);
   } else if (!strcmp(key, "profile")) {

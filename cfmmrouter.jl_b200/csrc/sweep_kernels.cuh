@@ -243,6 +243,7 @@ __global__ void scatter_trades_kernel(const double2* __restrict__ D,
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int64_t o = orig[i];
+  if (o < 0) return;  // padding pool
   outD[o] = D[i];
   outL[o] = L[i];
 }

@@ -24,8 +24,10 @@ def synth():
     return s
 
 
-def make_pools(cr, n, product=None, geomean=None, univ3=None, exact=None):
+def make_pools(cr, n, product=None, geomean=None, univ3=None, exact=None, pre=None):
     p = cr.DevicePools(n)
+    for k, val in (pre or {}).items():  # options that fix the layout (before finalize)
+        p.set_option(k, val)
     if product is not None:
         p.add_product(*product)
     if geomean is not None:
@@ -232,16 +234,44 @@ def test_inrange_math(cr):
 
 
 @pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5])
-@pytest.mark.parametrize("kind", ["near", "wide"])
-def test_product_gradient_sweep_variants(cr, oracle, synth, variant, kind):
-    m, n = 200_003, 3_001
+@pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7)])
+def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
+    """Every tile shape of the b-bucketed TMA kernel (several buckets at
+    n = 20011, one bucket at n = 7), and the first-generation kernel (-1)."""
     R, g, Ai = synth.product_pools(m, n, seed=variant + 10)
-    v = synth.dual_prices(n, kind)
-    p = make_pools(cr, n, product=(R, g, Ai))
-    p.set_option("tma_variant", variant)
+    p = make_pools(cr, n, product=(R, g, Ai), pre={"tma_variant": variant})
+    for kind in ("near", "wide"):
+        v = synth.dual_prices(n, kind)
+        psi, acc = p.sweep(v)
+        Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+        check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    # same layout, first-generation kernel
+    p.set_option("use_tma", 0)
     psi, acc = p.sweep(v)
-    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
     check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    # trades in insertion order despite the bucketed, padded device order
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+    with pytest.raises(cr.CFMMError):  # the layout is fixed at finalize
+        p.set_option("tma_variant", 0)
+    p.close()
+
+
+def test_update_reserves_bucketed_layout(cr, oracle, synth):
+    n = 9_000  # 3 buckets with the default tile shape
+    R, g, Ai = synth.product_pools(50_000, n, seed=21)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, product=(R, g, Ai))
+    R2 = R.copy()
+    R2[777:30_001] *= 0.75
+    p.update_reserves(0, 777, R2[777:30_001])
+    psi, acc = p.sweep(v)
+    Do, Lo = oracle.sweep_product(R2, g, Ai, v, threads=8)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
     p.close()
 
 

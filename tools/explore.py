@@ -41,6 +41,8 @@ def main():
 
     def run(tag, m, n, kind, nu_kind="near", iters=30, use_flush=False, **opts):
         p = cr.DevicePools(n)
+        if "tma_variant" in opts:
+            p.set_option("tma_variant", opts["tma_variant"])
         if kind == "product":
             p.add_product(*synth.product_pools(m, n))
             bpp = 32
@@ -53,7 +55,8 @@ def main():
             bpp = 32 + 16 * 4
         p.finalize()
         for k, v in opts.items():
-            p.set_option(k, v)
+            if k != "tma_variant":
+                p.set_option(k, v)
         if kind == "univ3":
             rng = np.random.default_rng(3)
             nu = np.exp(rng.uniform(np.log(0.5), np.log(2.0), size=n))
@@ -74,10 +77,9 @@ def main():
         run("c5 tma", M, N, "product", nu)
     for var in (1, 2, 3, 4, 5):
         run(f"c5 tma_variant={var}", M, N, "product", "near", tma_variant=var)
-    for bps in (1,):
-        run(f"c5 tma blocks_per_sm={bps}", M, N, "product", "near", blocks_per_sm=bps)
     run("c5 tma exact(generic in tma kernel)", M, N, "product", "near", exact=1)
-    run("c5 gen1", M, N, "product", "near", tma_variant=-1)
+    run("c5 gen1 (a-sorted)", M, N, "product", "near", tma_variant=-1)
+    run("c5 gen1 (bucketed layout)", M, N, "product", "near", use_tma=0)
     run("c2 tma L2-warm", 100_000, 1_000, "product", "near", iters=200)
     run("1M tma L2-warm", 1_000_000, 10_000, "product", "near", iters=100)
     return
