@@ -97,6 +97,8 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
+  int a_red_per_thread = 0;  // Ψ[a]: 0 = warp-aggregated RED per key, 1 = one RED per thread run
+  int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
   unsigned long long epoch = 0;
   DevBuf<unsigned long long> d_bad_epoch;
   int blocks_per_sm = 0;  // 0 = occupancy-derived
@@ -373,12 +375,12 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
-template <int V>
+template <int V, bool ECON>
 int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                            cudaStream_t st) {
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON>;
   static int occ = 0;
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -395,7 +397,8 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
-      (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch, s.in_fast_range ? 1 : 0, ctx->exact);
+      (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch, s.in_fast_range ? 1 : 0,
+      ctx->exact | (ctx->a_red_per_thread ? 16 : 0));
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;
@@ -403,14 +406,22 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
 
 int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                        cudaStream_t st) {
+  const bool econ = ctx->gradient_math != 0;
+#define CFMM_TMA_CASE(V)                                                          \
+  case V:                                                                         \
+    return econ ? launch_product_tma_cfg<V, true>(ctx, s, d_v, d_psi, st)         \
+                : launch_product_tma_cfg<V, false>(ctx, s, d_v, d_psi, st);
   switch (s.tma_variant) {
-    case 1: return launch_product_tma_cfg<1>(ctx, s, d_v, d_psi, st);
-    case 2: return launch_product_tma_cfg<2>(ctx, s, d_v, d_psi, st);
-    case 3: return launch_product_tma_cfg<3>(ctx, s, d_v, d_psi, st);
-    case 4: return launch_product_tma_cfg<4>(ctx, s, d_v, d_psi, st);
-    case 5: return launch_product_tma_cfg<5>(ctx, s, d_v, d_psi, st);
-    default: return launch_product_tma_cfg<0>(ctx, s, d_v, d_psi, st);
+    CFMM_TMA_CASE(1)
+    CFMM_TMA_CASE(2)
+    CFMM_TMA_CASE(3)
+    CFMM_TMA_CASE(4)
+    CFMM_TMA_CASE(5)
+    default:
+      return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
+                  : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);
   }
+#undef CFMM_TMA_CASE
 }
 
 int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
@@ -758,6 +769,10 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "a_red_per_thread")) {
+    ctx->a_red_per_thread = value != 0;
+  } else if (!strcmp(key, "gradient_math")) {
+    ctx->gradient_math = value != 0;
   } else if (!strcmp(key, "use_tma")) {
     ctx->use_tma = value != 0;
   } else if (!strcmp(key, "debug_skip")) {

@@ -134,7 +134,12 @@ int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
  * path that evaluates only the non-zero side, falling back to the full form
  * near ties), "blocks_per_sm" (0 = occupancy-derived), "profile" (see
  * cfmm_profile_read), "tma_variant" (tile shape of the ProductTwoCoin TMA
- * kernel; -1 = first-generation kernel). */
+ * kernel, fixed at cfmm_finalize; -1 = first-generation kernel only),
+ * "use_tma" (0 = first-generation kernel on the same layout),
+ * "gradient_math" (gradient-only ProductTwoCoin sweeps, where per-pool trades
+ * are not observable: 1 = default, economized closed form, <= ~3 ulp of the
+ * reserve per pool; 0 = the reference's operation order, bit-identical per
+ * pool.  Materialising sweeps and "exact" are always bit-identical). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
 /* Device time (ms, CUDA events on the sweep stream) of the kernels of the
