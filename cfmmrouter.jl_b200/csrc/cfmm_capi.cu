@@ -97,7 +97,7 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
-  int a_red_per_thread = 0;  // Ψ[a]: 0 = warp-aggregated RED per key, 1 = one RED per thread run
+  int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
   unsigned long long epoch = 0;
   DevBuf<unsigned long long> d_bad_epoch;
@@ -177,10 +177,10 @@ struct TmaVariant {
 constexpr TmaVariant kTmaVariants[] = {
     {256, 3, 2, 3200, 2},  // 0 (default): 98 KB smem, 2 CTAs/SM
     {256, 5, 2, 2048, 2},  // 1: 112 KB, 2 CTAs/SM
-    {384, 3, 2, 2048, 2},  // 2: 104 KB, 2 CTAs/SM, 24 warps
+    {256, 3, 3, 1600, 2},  // 2: 97 KB, 2 CTAs/SM, 3 stages
     {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
     {256, 3, 2, 1600, 3},  // 4: 73 KB, 3 CTAs/SM, 24 warps
-    {256, 5, 2, 3200, 1},  // 5: 130 KB, 1 CTA/SM
+    {512, 3, 3, 3200, 1},  // 5: 195 KB, 1 CTA/SM, 3 stages
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
@@ -398,7 +398,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
       (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch, s.in_fast_range ? 1 : 0,
-      ctx->exact | (ctx->a_red_per_thread ? 16 : 0));
+      ctx->exact | (ctx->a_red_per_thread ? 0 : 16));
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;

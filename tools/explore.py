@@ -77,9 +77,7 @@ def main():
         run("c5 tma", M, N, "product", nu)
     for var in (1, 2, 3, 4, 5):
         run(f"c5 tma_variant={var}", M, N, "product", "near", tma_variant=var)
-    run("c5 tma a_red_per_thread", M, N, "product", "near", a_red_per_thread=1)
-    run("c5 tma v1 a_red_per_thread", M, N, "product", "near", tma_variant=1, a_red_per_thread=1)
-    run("c5 tma v4 a_red_per_thread", M, N, "product", "near", tma_variant=4, a_red_per_thread=1)
+    run("c5 tma warp-aggregated a-RED", M, N, "product", "near", a_red_per_thread=0)
     run("c5 tma reference-order math", M, N, "product", "near", gradient_math=0)
     run("c5 tma v1 reference-order math", M, N, "product", "near", tma_variant=1, gradient_math=0)
     run("c5 tma exact(generic in tma kernel)", M, N, "product", "near", exact=1)
