@@ -181,6 +181,9 @@ constexpr TmaVariant kTmaVariants[] = {
     {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
     {256, 3, 2, 1600, 3},  // 4: 73 KB, 3 CTAs/SM, 24 warps
     {512, 3, 3, 3200, 1},  // 5: 195 KB, 1 CTA/SM, 3 stages
+    {768, 3, 2, 3200, 1},  // 6: 195 KB, 1 CTA/SM, 24 warps
+    {768, 2, 2, 3200, 1},  // 7: 147 KB, 1 CTA/SM, 24 warps, 2 pools/thread
+    {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
@@ -417,6 +420,9 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(3)
     CFMM_TMA_CASE(4)
     CFMM_TMA_CASE(5)
+    CFMM_TMA_CASE(6)
+    CFMM_TMA_CASE(7)
+    CFMM_TMA_CASE(8)
     default:
       return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
                   : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);
