@@ -1,18 +1,26 @@
 // peer_exchange.cuh -- sum-allreduce of [Ψ ; acc] (n_tokens+1 fp64) across the
 // GPUs of one box, over NVLink peer memory (no NCCL on this path).
 //
-// Why not NCCL: the message is 8 KB .. 400 KB, i.e. purely latency-bound, and a
-// sharded sweep kernel runs for only a few microseconds; NCCL's small-message
-// latency would dominate the step.  Here every rank publishes its partial
-// vector in a peer-mapped slot, raises one flag per peer, and pulls the other
-// ranks' partials straight over NVLink, summing in rank order -- so every rank
-// ends with the bitwise-identical vector (the replicated L-BFGS-B drivers stay
-// in lock-step), with a single flag round per reduction.
+// The message is 8 KB .. 400 KB: purely latency-bound.  Protocol ("LL push",
+// the idea NCCL's low-latency protocol uses): every rank WRITES its partial
+// vector straight into a receive area in each peer's memory as
+// self-validating packets -- each fp64 travels as two 8-byte words
+// {hi32 | epoch32}, {lo32 | epoch32} (8-byte stores are single-copy atomic, so a
+// word is either old or complete).  The receiver polls its own local memory
+// until both words of a packet carry the current epoch, then adds the value.
+// There is no flag, no fence and no grid barrier on the critical path: one
+// NVLink traversal, and the reduction runs as packets land.  Ranks are summed
+// in rank order, so every rank ends with the bitwise-identical vector (the
+// replicated L-BFGS-B drivers stay in lock-step).
 //
-// Slots are double-buffered by epoch parity: a rank can only start writing
-// epoch e+2 after it saw every peer's flag for e+1, and a peer raises e+1 only
-// after its epoch-e kernel (the reader of slot e) has completed in stream
-// order, so no reader can still be on the slot that is being overwritten.
+// The first version of this file (flag + pull over peer loads, system fences)
+// measured 24 us per exchange at 2 GPUs against ~15 us for ncclAllReduce; see
+// DESIGN.md for the numbers of this one.
+//
+// Receive areas are double-buffered by epoch parity.  A rank pushes epoch e+2
+// only after finishing exchange e+1, i.e. after receiving every peer's e+1
+// packets, which a peer sends only after its own exchange e completed in stream
+// order -- so nobody can still be reading the area that is being overwritten.
 //
 // Mapping: one process per GPU -> cudaIpc handles exchanged by the host side;
 // several contexts in one process -> raw pointers + cudaDeviceEnablePeerAccess.
@@ -27,85 +35,64 @@
 namespace cfmm {
 
 constexpr int kMaxPeers = 16;
-constexpr int kExchangeThreads = 512;
+constexpr int kExchangeThreads = 256;
 
 struct PeerHandle {
   cudaIpcMemHandle_t ipc;  // 64 B
   uint64_t raw_ptr;        // same-process shortcut
-  int64_t len;             // doubles per slot
+  int64_t len;             // doubles per vector
   int32_t pid;
   int32_t device;
+  int32_t world_cap;       // receive areas allocated for this many ranks
+  int32_t pad;
 };
 
-// Layout of a rank's exchange buffer (all offsets in bytes from base):
-//   [0, 1024)                 flags[kMaxPeers] (uint64, one 64 B line each)
-//   [1024, 1024 + 2*len*8)    slot[0], slot[1]
+// Receive buffer of a rank: area(src, parity) = base + ((src*2 + parity) * len) ulonglong2
 struct ExchangeView {
-  unsigned long long* flags;             // local: flags[p*8] = last epoch published by rank p
-  double* my_slot[2];                    // local slots
-  const double* peer_slot[kMaxPeers][2]; // peer-mapped (own entry = local)
-  unsigned long long* peer_flags[kMaxPeers];  // peer-mapped flag arrays
-  unsigned int* arrive;                  // local grid-arrival counter
+  ulonglong2* recv_local;             // this rank's receive buffer
+  ulonglong2* recv_peer[kMaxPeers];   // peer-mapped receive buffers (own entry unused)
   int world, rank;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p,
-                                               unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_packet(ulonglong2* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(
-    const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ ulonglong2 ld_packet(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
 
-// grid must be fully co-resident (it spins); launched with <= sm_count CTAs.
 __global__ void __launch_bounds__(kExchangeThreads)
     peer_allreduce_kernel(ExchangeView x, double* __restrict__ data, int64_t len,
-                          unsigned long long epoch) {
-  const int par = (int)(epoch & 1ull);
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                          unsigned int epoch) {
+  const int par = (int)(epoch & 1u);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-
-  // phase 1: publish my partial
-  double* slot = x.my_slot[par];
-  for (int64_t j = tid; j < len; j += stride) slot[j] = data[j];
-  __syncthreads();
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned int prev = atomicAdd(x.arrive, 1u);
-    s_last = (prev == (unsigned int)(epoch * gridDim.x) - 1u);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < x.world) {
-    // every CTA of this rank has published (their fences precede the atomic)
-    __threadfence_system();
-    st_release_sys(x.peer_flags[threadIdx.x] + 8 * x.rank, epoch);
-  }
-
-  // phase 2: wait for every rank's flag, then pull and sum in rank order
-  if (threadIdx.x < x.world) {
-    const unsigned long long* f = x.flags + 8 * threadIdx.x;
-    while (ld_acquire_sys(f) < epoch) {
-    }
-  }
-  __syncthreads();
-  for (int64_t j = tid; j < len; j += stride) {
-    double v[kMaxPeers];
+  const unsigned long long tag = (unsigned long long)epoch;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
+    const double mine = data[j];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+    const unsigned long long w0 = ((bits >> 32) << 32) | tag;         // {hi32 | epoch}
+    const unsigned long long w1 = ((bits & 0xffffffffull) << 32) | tag;  // {lo32 | epoch}
+    // push to every peer's area for source = me
 #pragma unroll
     for (int p = 0; p < kMaxPeers; ++p)
-      if (p < x.world) v[p] = ld_relaxed_sys(x.peer_slot[p][par] + j);
+      if (p < x.world && p != x.rank)
+        st_packet(x.recv_peer[p] + ((int64_t)(x.rank * 2 + par) * len + j), w0, w1);
+    // gather: poll my own areas, sum in rank order
     double s = 0.0;
 #pragma unroll
-    for (int p = 0; p < kMaxPeers; ++p)
-      if (p < x.world) s += v[p];
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p >= x.world) continue;
+      if (p == x.rank) {
+        s += mine;
+        continue;
+      }
+      const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * len + j);
+      ulonglong2 v = ld_packet(q);
+      while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+      s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
+    }
     data[j] = s;
   }
 }
@@ -119,11 +106,9 @@ class PeerExchange {
   bool export_handle(int64_t len, PeerHandle* out) {
     if (!base_) {
       len_ = len;
-      bytes_ = 1024 + 2 * (size_t)len * sizeof(double);
+      bytes_ = (size_t)kMaxPeers * 2 * (size_t)len * sizeof(ulonglong2);
       if (!ok(cudaMalloc(&base_, bytes_), "cudaMalloc(exchange)")) return false;
       if (!ok(cudaMemset(base_, 0, bytes_), "cudaMemset(exchange)")) return false;
-      if (!ok(cudaMalloc(&arrive_, sizeof(unsigned int)), "cudaMalloc(arrive)")) return false;
-      if (!ok(cudaMemset(arrive_, 0, sizeof(unsigned int)), "cudaMemset(arrive)")) return false;
     }
     memset(out, 0, sizeof(*out));
     if (!ok(cudaIpcGetMemHandle(&out->ipc, base_), "cudaIpcGetMemHandle")) return false;
@@ -133,6 +118,7 @@ class PeerExchange {
     int dev = 0;
     cudaGetDevice(&dev);
     out->device = dev;
+    out->world_cap = kMaxPeers;
     return true;
   }
 
@@ -144,16 +130,16 @@ class PeerExchange {
     }
     world_ = world;
     rank_ = rank;
-    grid_ = sm_count < 64 ? sm_count : 64;
+    // every element is an independent push+poll: enough CTAs to cover the vector once
+    int64_t want = (len_ + kExchangeThreads - 1) / kExchangeThreads;
+    grid_ = (int)(want < 2 * sm_count ? want : 2 * sm_count);
+    if (grid_ < 1) grid_ = 1;
     int my_dev = 0;
     cudaGetDevice(&my_dev);
     memset(&view_, 0, sizeof(view_));
     view_.world = world;
     view_.rank = rank;
-    view_.arrive = arrive_;
-    view_.flags = (unsigned long long*)base_;
-    view_.my_slot[0] = (double*)((char*)base_ + 1024);
-    view_.my_slot[1] = view_.my_slot[0] + len_;
+    view_.recv_local = (ulonglong2*)base_;
     for (int p = 0; p < world; ++p) {
       PeerHandle h;
       memcpy(&h, handles + (size_t)p * stride, sizeof(h));
@@ -183,9 +169,7 @@ class PeerExchange {
           return false;
         opened_[p] = pbase;
       }
-      view_.peer_flags[p] = (unsigned long long*)pbase;
-      view_.peer_slot[p][0] = (const double*)((char*)pbase + 1024);
-      view_.peer_slot[p][1] = view_.peer_slot[p][0] + len_;
+      view_.recv_peer[p] = (ulonglong2*)pbase;
     }
     epoch_ = 0;
     attached_ = true;
@@ -198,6 +182,7 @@ class PeerExchange {
       return false;
     }
     ++epoch_;
+    if (epoch_ == 0) epoch_ = 2;  // 0 is the value of untouched memory; keep parity moving
     peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, data, len, epoch_);
     return ok(cudaGetLastError(), "peer_allreduce_kernel launch");
   }
@@ -209,9 +194,7 @@ class PeerExchange {
         opened_[p] = nullptr;
       }
     if (base_) cudaFree(base_);
-    if (arrive_) cudaFree(arrive_);
     base_ = nullptr;
-    arrive_ = nullptr;
     attached_ = false;
     world_ = 1;
   }
@@ -223,12 +206,11 @@ class PeerExchange {
     return false;
   }
   void* base_ = nullptr;
-  unsigned int* arrive_ = nullptr;
   void* opened_[kMaxPeers] = {};
   size_t bytes_ = 0;
   int64_t len_ = 0;
   int world_ = 1, rank_ = 0, grid_ = 64;
-  unsigned long long epoch_ = 0;
+  unsigned int epoch_ = 0;
   bool attached_ = false;
   ExchangeView view_;
   std::string err_;
