@@ -184,6 +184,9 @@ constexpr TmaVariant kTmaVariants[] = {
     {768, 3, 2, 3200, 1},  // 6: 195 KB, 1 CTA/SM, 24 warps
     {768, 2, 2, 3200, 1},  // 7: 147 KB, 1 CTA/SM, 24 warps, 2 pools/thread
     {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
+    {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
+    {320, 3, 2, 3200, 2},  // 10: 110 KB, 2 CTAs/SM, 20 warps (<= 102 regs)
+    {352, 3, 2, 2400, 2},  // 11: 104 KB, 2 CTAs/SM, 22 warps (<= 93 regs)
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
@@ -423,6 +426,9 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(6)
     CFMM_TMA_CASE(7)
     CFMM_TMA_CASE(8)
+    CFMM_TMA_CASE(9)
+    CFMM_TMA_CASE(10)
+    CFMM_TMA_CASE(11)
     default:
       return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
                   : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);

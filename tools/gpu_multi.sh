@@ -12,4 +12,4 @@ done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 1000 --warmup 10 --scaling strong > gpurun_out/bench_n2_strong.json 2> gpurun_out/bench_n2_strong.err
 cat gpurun_out/bench_n2_strong.json; tail -3 gpurun_out/bench_n2_strong.err
 timeout 300 python bench.py --steps 1000 --warmup 10 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
-timeout 600 python tools/explore.py > gpurun_out/explore.log 2>&1; cat gpurun_out/explore.log
+
