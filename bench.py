@@ -259,6 +259,7 @@ def run_ours(args):
         pools.add_univ3(*shard["univ3"])
     pools.finalize()
     pools.set_option("exact", args.exact)
+    pools.set_option("sweep_events", 0)
     m_local = shard["m_local"]
     alg_bytes = float(shard["bytes"])
     del shard
@@ -286,35 +287,43 @@ def run_ours(args):
     sptr = stream.cuda_stream
 
     def step():
-        pools.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, sptr)
-        if exchange == "nccl":
+        if exchange == "nccl":  # NCCL needs the partial in a torch tensor
+            pools.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, sptr)
             dist.all_reduce(d_psi)
+        else:  # zero-copy: [Ψ; acc] stays in the context's device buffer
+            pools.sweep_device_view(d_nu.data_ptr(), False, sptr)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_region(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup)):
             step()
         barrier()
-        # arm per-kernel event timing for the timed region
-        n_kernels = 2 if m_local and args.workload.startswith("config3") else 1
-        pools.set_option("profile", args.steps * (n_kernels + (1 if exchange == "peer" else 0)))
+        # ---- timed region 1: K steps, nothing but the sweeps on the stream -> `value`
         l0 = pools.launch_count
         sampler = ClockSampler(local_rank)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
         sampler.start()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        barrier()
+        ms_total = timed_region(args.steps)
         sampler.stop()
-        ms_total = e0.elapsed_time(e1)
         launches = pools.launch_count - l0
+        # ---- timed region 2: the same K steps with a CUDA-event pair around every
+        # kernel launch (on the launching stream) -> per-kernel durations for `roofline`
+        n_kernels = 2 if args.workload.startswith("config3") else 1
+        pools.set_option("profile", args.steps * (n_kernels + (1 if exchange == "peer" else 0)))
+        timed_region(args.steps)
         prof = {t: pools.profile_read(t) for t in (0, 1, 2, 3)}
         pools.set_option("profile", 0)
 

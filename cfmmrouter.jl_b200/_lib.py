@@ -42,6 +42,7 @@ SYMBOLS = {
     "cfmm_num_tokens": (C.c_int64, [_ctx]),
     "cfmm_sweep": (C.c_int, [_ctx, _dp, _dp, _dp, C.c_int]),
     "cfmm_sweep_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "cfmm_sweep_device_view": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cfmm_get_trades": (C.c_int, [_ctx, _dp, _dp]),
     "cfmm_update_reserves": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _dp]),
     "cfmm_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),

@@ -97,10 +97,12 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
+  int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
   int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
-  unsigned long long epoch = 0;
-  DevBuf<unsigned long long> d_bad_epoch;
+  unsigned long long epoch = 0;  // sweeps enqueued so far
+  DevBuf<double> d_accum[2];     // ping-pong [Ψ; acc] accumulators, zeroed one sweep ahead in-kernel
+  double* zero_pending = nullptr; // accumulator the first kernel of the current sweep must zero
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   int64_t launches = 0;
   std::string err;
@@ -175,7 +177,7 @@ struct TmaVariant {
   int threads, L, S, nbmax, minb;
 };
 constexpr TmaVariant kTmaVariants[] = {
-    {256, 3, 2, 3200, 2},  // 0 (default): 98 KB smem, 2 CTAs/SM
+    {320, 3, 2, 3200, 2},  // 0 (default): 110 KB smem, 2 CTAs/SM, 20 warps, 100 regs (no spill)
     {256, 5, 2, 2048, 2},  // 1: 112 KB, 2 CTAs/SM
     {256, 3, 3, 1600, 2},  // 2: 97 KB, 2 CTAs/SM, 3 stages
     {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
@@ -185,7 +187,7 @@ constexpr TmaVariant kTmaVariants[] = {
     {768, 2, 2, 3200, 1},  // 7: 147 KB, 1 CTA/SM, 24 warps, 2 pools/thread
     {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
     {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
-    {320, 3, 2, 3200, 2},  // 10: 110 KB, 2 CTAs/SM, 20 warps (<= 102 regs)
+    {256, 3, 2, 3200, 2},  // 10: 98 KB, 2 CTAs/SM, 16 warps
     {352, 3, 2, 2400, 2},  // 11: 104 KB, 2 CTAs/SM, 22 warps (<= 93 regs)
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
@@ -320,6 +322,13 @@ int upload_set(cfmm_ctx* ctx, int type) {
   return CFMM_OK;
 }
 
+// the first kernel of a sweep zeroes the other ping-pong accumulator
+inline double* take_zero_pending(cfmm_ctx* ctx) {
+  double* p = ctx->zero_pending;
+  ctx->zero_pending = nullptr;
+  return p;
+}
+
 // profiling: bracket one launch with events on its stream
 struct ProfScope {
   cfmm_ctx* ctx;
@@ -370,11 +379,11 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   if (mat) {
     cfmm::sweep_kernel<P, true, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
         pools, d_v, d_psi, (int)ctx->n_tokens, s.d_outD.p, s.d_outL.p, m_all,
-        ctx->exact | (ctx->debug_skip << 1));
+        ctx->exact | (ctx->debug_skip << 1), take_zero_pending(ctx));
   } else {
     cfmm::sweep_kernel<P, false, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
         pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, m_all,
-        ctx->exact | (ctx->debug_skip << 1));
+        ctx->exact | (ctx->debug_skip << 1), take_zero_pending(ctx));
   }
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -403,7 +412,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
-      (int)ctx->n_tokens, ctx->d_bad_epoch.p, ctx->epoch, s.in_fast_range ? 1 : 0,
+      (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0,
       ctx->exact | (ctx->a_red_per_thread ? 0 : 16));
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -436,19 +445,18 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
 #undef CFMM_TMA_CASE
 }
 
-int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
-                  cudaStream_t st) {
-  CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-  // zero [Ψ; acc] and validate ν for the guard-free math (one small kernel)
+// One sweep.  The kernels accumulate into the internal ping-pong accumulator
+// of this sweep (already zero: the previous sweep's first kernel cleared it) and
+// clear the other one for the next sweep.  The result goes to d_dst if given
+// (peer exchange writes it there directly; single GPU: one D2D copy), else it
+// stays in the accumulator; *view receives the device pointer that holds it.
+int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
+                  cudaStream_t st, const double** view) {
+  if (ctx->sweep_events) CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
   ctx->epoch++;
-  {
-    const int threads = 256;
-    const int blocks = (int)((ctx->n_tokens + 1 + threads - 1) / threads);
-    cfmm::prepare_sweep_kernel<<<blocks, threads, 0, st>>>(d_v, d_psi, (int)ctx->n_tokens,
-                                                         ctx->d_bad_epoch.p, ctx->epoch);
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-  }
+  double* d_psi = ctx->d_accum[ctx->epoch & 1].p;
+  ctx->zero_pending = ctx->d_accum[(ctx->epoch + 1) & 1].p;
+  const size_t acc_bytes = (size_t)(ctx->n_tokens + 1) * sizeof(double);
   int rc;
   {
     PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
@@ -479,14 +487,24 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_psi, bool mat,
       if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
+  if (ctx->zero_pending) {  // no kernel ran (empty pool set): clear the other accumulator here
+    CU_TRY(ctx, cudaMemsetAsync(take_zero_pending(ctx), 0, acc_bytes, st));
+  }
+  const double* result = d_psi;
   if (ctx->comm.attached()) {
     ProfScope prof(ctx, 3, st);
-    if (!ctx->comm.all_reduce(d_psi, ctx->n_tokens + 1, st))
+    double* dst = d_dst ? d_dst : d_psi;
+    if (!ctx->comm.all_reduce(d_psi, dst, ctx->n_tokens + 1, st))
       return fail(ctx, CFMM_ERR_COMM, "peer exchange failed: %s",
                   ctx->comm.error().c_str());
     ctx->launches += ctx->comm.launches_per_reduce();
+    result = dst;
+  } else if (d_dst) {
+    CU_TRY(ctx, cudaMemcpyAsync(d_dst, d_psi, acc_bytes, cudaMemcpyDeviceToDevice, st));
+    result = d_dst;
   }
-  CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+  if (view) *view = result;
+  if (ctx->sweep_events) CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
   if (mat) ctx->has_trades = true;
   return CFMM_OK;
 }
@@ -547,8 +565,10 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   CREATE_TRY(cudaEventCreate(&ctx->ev1));
   CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
   CREATE_TRY(ctx->d_psi.alloc((size_t)n_tokens + 1));
-  CREATE_TRY(ctx->d_bad_epoch.alloc(1));
-  CREATE_TRY(cudaMemset(ctx->d_bad_epoch.p, 0, sizeof(unsigned long long)));
+  for (auto& a : ctx->d_accum) {
+    CREATE_TRY(a.alloc((size_t)n_tokens + 1));
+    CREATE_TRY(cudaMemset(a.p, 0, ((size_t)n_tokens + 1) * sizeof(double)));
+  }
   CREATE_TRY(cudaMallocHost((void**)&ctx->h_stage, (size_t)(n_tokens + 1) * sizeof(double)));
 #undef CREATE_TRY
   *out = ctx;
@@ -565,7 +585,8 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_psi.release();
-  ctx->d_bad_epoch.release();
+  ctx->d_accum[0].release();
+  ctx->d_accum[1].release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -656,7 +677,17 @@ int cfmm_sweep_device(cfmm_ctx* ctx, const double* d_v, double* d_psi_acc,
   if (!d_v || !d_psi_acc) return fail(ctx, CFMM_ERR_INVALID, "null device pointer");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return enqueue_sweep(ctx, d_v, d_psi_acc, materialize != 0, st);
+  return enqueue_sweep(ctx, d_v, d_psi_acc, materialize != 0, st, nullptr);
+}
+
+int cfmm_sweep_device_view(cfmm_ctx* ctx, const double* d_v, int materialize, void* stream,
+                           const double** d_psi_acc_out) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!d_v || !d_psi_acc_out) return fail(ctx, CFMM_ERR_INVALID, "null pointer");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return enqueue_sweep(ctx, d_v, nullptr, materialize != 0, st, d_psi_acc_out);
 }
 
 int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
@@ -669,10 +700,11 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   const size_t nb = (size_t)ctx->n_tokens * sizeof(double);
   cudaStream_t st = ctx->stream;
   CU_TRY(ctx, cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st));
-  rc = enqueue_sweep(ctx, ctx->d_nu.p, ctx->d_psi.p, materialize != 0, st);
+  const double* res = nullptr;
+  rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, materialize != 0, st, &res);
   if (rc != CFMM_OK) return rc;
-  CU_TRY(ctx, cudaMemcpyAsync(psi_out, ctx->d_psi.p, nb, cudaMemcpyDeviceToHost, st));
-  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, ctx->d_psi.p + ctx->n_tokens,
+  CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb, cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, res + ctx->n_tokens,
                               sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   *acc_out = ctx->h_stage[0];
@@ -781,6 +813,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "sweep_events")) {
+    ctx->sweep_events = value != 0;
   } else if (!strcmp(key, "a_red_per_thread")) {
     ctx->a_red_per_thread = value != 0;
   } else if (!strcmp(key, "gradient_math")) {

@@ -64,13 +64,13 @@ __device__ __forceinline__ ulonglong2 ld_packet(const ulonglong2* p) {
 }
 
 __global__ void __launch_bounds__(kExchangeThreads)
-    peer_allreduce_kernel(ExchangeView x, double* __restrict__ data, int64_t len,
+    peer_allreduce_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
                           unsigned int epoch) {
   const int par = (int)(epoch & 1u);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const unsigned long long tag = (unsigned long long)epoch;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
-    const double mine = data[j];
+    const double mine = src[j];
     const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
     const unsigned long long w0 = ((bits >> 32) << 32) | tag;         // {hi32 | epoch}
     const unsigned long long w1 = ((bits & 0xffffffffull) << 32) | tag;  // {lo32 | epoch}
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kExchangeThreads)
       while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
       s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
     }
-    data[j] = s;
+    dst[j] = s;
   }
 }
 
@@ -176,14 +176,14 @@ class PeerExchange {
     return true;
   }
 
-  bool all_reduce(double* data, int64_t len, cudaStream_t st) {
+  bool all_reduce(const double* src, double* dst, int64_t len, cudaStream_t st) {
     if (len != len_) {
       err_ = "all_reduce length mismatch";
       return false;
     }
     ++epoch_;
     if (epoch_ == 0) epoch_ = 2;  // 0 is the value of untouched memory; keep parity moving
-    peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, data, len, epoch_);
+    peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
     return ok(cudaGetLastError(), "peer_allreduce_kernel launch");
   }
 

@@ -164,7 +164,12 @@ template <class P, bool MAT, int U>
 __global__ void __launch_bounds__(kSweepThreads)
     sweep_kernel(P pools, const double* __restrict__ nu, double* __restrict__ psi,
                  int n_tokens, double2* __restrict__ outD,
-                 double2* __restrict__ outL, int64_t m, int flags) {
+                 double2* __restrict__ outL, int64_t m, int flags,
+                 double* __restrict__ zero_next) {
+  // zero the accumulator the NEXT sweep will use (ping-pong; replaces a memset launch)
+  if (zero_next)
+    for (int i = blockIdx.x * kSweepThreads + threadIdx.x; i <= n_tokens; i += gridDim.x * kSweepThreads)
+      zero_next[i] = 0.0;
   // flags: bit0 = exact (all four closed forms); bits 1-3 are measurement
   // switches (skip the Ψ[b] RED / the Ψ[a] segmented RED / the acc fold) used
   // only by tools/explore.py to attribute time; the product never sets them.

@@ -118,6 +118,14 @@ class DevicePools:
         self._chk(self._lib.cfmm_sweep_device(self._ctx, d_v_ptr, d_psi_acc_ptr,
                                               1 if materialize else 0, stream_ptr or None))
 
+    def sweep_device_view(self, d_v_ptr: int, materialize: bool = False, stream_ptr: int = 0) -> int:
+        """Zero-copy device sweep: returns the device address of [psi; acc]
+        (valid until the next sweep on this context)."""
+        out = C.c_void_p()
+        self._chk(self._lib.cfmm_sweep_device_view(self._ctx, d_v_ptr, 1 if materialize else 0,
+                                                   stream_ptr or None, C.byref(out)))
+        return int(out.value)
+
     def last_sweep_ms(self) -> float:
         ms = C.c_float(0.0)
         self._chk(self._lib.cfmm_last_sweep_ms(self._ctx, C.byref(ms)))

@@ -118,6 +118,14 @@ int cfmm_sweep(cfmm_ctx *ctx, const double *v, double *psi_out,
 int cfmm_sweep_device(cfmm_ctx *ctx, const double *d_v, double *d_psi_acc,
                       int materialize, void *stream);
 
+/* Zero-copy form: the result stays in a context-owned device buffer and
+ * *d_psi_acc_out receives its address ([n_tokens + 1] fp64).  The buffer is
+ * valid until the next sweep on this context is enqueued (two internal
+ * accumulators alternate; each sweep clears the other one in-kernel, so no
+ * memset or copy is launched). */
+int cfmm_sweep_device_view(cfmm_ctx *ctx, const double *d_v, int materialize,
+                           void *stream, const double **d_psi_acc_out);
+
 /* Trades of the last materialising sweep, in global insertion order:
  * Delta, Lambda: host [2 * cfmm_num_pools] pool-major (r.Δs[i], r.Λs[i]). */
 int cfmm_get_trades(cfmm_ctx *ctx, double *Delta, double *Lambda);

@@ -282,6 +282,46 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
     p.close()
 
 
+def test_device_resident_api(cr, oracle, synth):
+    """cfmm_sweep_device (caller's buffer) and cfmm_sweep_device_view (zero-copy,
+    ping-pong accumulators cleared in-kernel) over many consecutive sweeps."""
+    import torch
+    n = 7_001
+    R, g, Ai = synth.product_pools(150_000, n, seed=31)
+    Rg, gg, Ag, wg = synth.geomean_pools(20_000, n, seed=32)
+    p = make_pools(cr, n, product=(R, g, Ai), geomean=(Rg, gg, Ag, wg))
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    out = torch.full((n + 1,), 7.0, dtype=torch.float64, device=dev)  # must be overwritten, not accumulated
+    for k, kind in enumerate(["wide", "near", "ones", "wide", "near"]):
+        v = synth.dual_prices(n, kind, seed=k)
+        d_v = torch.from_numpy(v).to(dev)
+        D1, L1 = oracle.sweep_product(R, g, Ai, v, threads=8)
+        p.sweep(v, materialize=True)  # geomean reference = the GPU's own per-pool trades
+        D, L = p.trades()
+        assert np.array_equal(D[:150_000], D1)
+        A = np.concatenate([Ai, Ag])
+        p.sweep_device(d_v.data_ptr(), out.data_ptr(), False, stream)
+        torch.cuda.synchronize()
+        h = out.cpu().numpy()
+        check_psi(oracle, A, D, L, v, n, h[:n], float(h[n]), R=np.concatenate([R, Rg]), g=np.concatenate([g, gg]))
+        ptr = p.sweep_device_view(d_v.data_ptr(), False, stream)
+        torch.cuda.synchronize()
+        # read the context-owned buffer through torch: wrap the raw pointer
+        check = _from_ptr(torch, ptr, n + 1, dev).clone().cpu().numpy()
+        check_psi(oracle, A, D, L, v, n, check[:n], float(check[n]), R=np.concatenate([R, Rg]), g=np.concatenate([g, gg]))
+    p.close()
+
+
+def _from_ptr(torch, ptr, count, dev):
+    """A float64 torch view of `count` elements at a raw device pointer."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=dev)
+
+
 def test_update_reserves_bucketed_layout(cr, oracle, synth):
     n = 9_000  # 3 buckets with the default tile shape
     R, g, Ai = synth.product_pools(50_000, n, seed=21)
