@@ -188,7 +188,7 @@ constexpr TmaVariant kTmaVariants[] = {
     {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
     {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
     {256, 3, 2, 3200, 2},  // 10: 98 KB, 2 CTAs/SM, 16 warps
-    {352, 3, 2, 2400, 2},  // 11: 104 KB, 2 CTAs/SM, 22 warps (<= 93 regs)
+    {288, 3, 3, 1600, 2},  // 11: 106 KB, 2 CTAs/SM, 18 warps, 3 stages
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
