@@ -183,6 +183,51 @@ __device__ __forceinline__ Trade geomean_arb(double R1, double R2, double w1,
   return geomean_full(R1, R2, w1, w2, g, v1, v2);
 }
 
+// Economized GeometricMean trade for gradient-only sweeps (per-pool values not
+// observable; see product_tma.cuh for the argument).  With the traded side
+// chosen as above, t = num/den = γ·m·e·r1/r2 > 1 and u = t^(1/(e+1)):
+//     Δ_tendered = r2·(u − 1)/γ ,   Λ_received = r1·(1 − u/t)
+// which is src/cfmms.jl:180-181 with r2 and r1 factored out of the powers
+// (1/(e+1) = w_received/(w1+w2)).  One pow instead of four.
+__device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w1,
+                                                  double w2, double g, double v1,
+                                                  double v2) {
+  const double uA = __dmul_rn(__dmul_rn(v1, w2), R1);
+  const double uB = __dmul_rn(__dmul_rn(v2, w1), R2);
+  const double tA = __dmul_rn(g, uB);
+  const double tB = __dmul_rn(g, uA);
+  const double eta = __ddiv_rn(w1, w2);
+  const bool sane = in_geo_range(R1) && in_geo_range(R2) && in_geo_range(v1) &&
+                    in_geo_range(v2) && in_geo_range(g) && (eta > 1.0 / 24.0) && (eta < 24.0);
+  const bool zA = tA < __dmul_rn(uA, kGeoLo);
+  const bool zB = tB < __dmul_rn(uB, kGeoLo);
+  const bool fA = (tA > __dmul_rn(uA, kGeoHi)) && zB;
+  const bool fB = (tB > __dmul_rn(uB, kGeoHi)) && zA;
+  Trade t;
+  t.d1 = t.d2 = t.l1 = t.l2 = 0.0;
+  if (sane && (fA || fB)) {
+    const double num = fA ? tA : tB;
+    const double den = fA ? uA : uB;
+    const double ra = fA ? R1 : R2;  // reserve of the tendered token
+    const double rb = fA ? R2 : R1;  // reserve of the received token
+    const double ratio = num / den;
+    const double ex = (fA ? w2 : w1) / (w1 + w2);
+    const double u = pow(ratio, ex);
+    const double d = ra * (u - 1.0) / g;
+    const double l = rb * (1.0 - u / ratio);
+    if (fA) {
+      t.d1 = d;
+      t.l2 = l;
+    } else {
+      t.d2 = d;
+      t.l1 = l;
+    }
+    return t;
+  }
+  if (sane && zA && zB) return t;
+  return geomean_full(R1, R2, w1, w2, g, v1, v2);
+}
+
 // ---------------------------------------------------------------------------
 // UniV3 -- src/cfmms.jl:251-259, 272-289, 294-313, 321-337, 339-395
 // ---------------------------------------------------------------------------

@@ -383,7 +383,7 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   } else {
     cfmm::sweep_kernel<P, false, U><<<(unsigned)blocks, cfmm::kSweepThreads, 0, st>>>(
         pools, d_v, d_psi, (int)ctx->n_tokens, nullptr, nullptr, m_all,
-        ctx->exact | (ctx->debug_skip << 1), take_zero_pending(ctx));
+        ctx->exact | (ctx->debug_skip << 1) | (ctx->gradient_math ? 16 : 0), take_zero_pending(ctx));
   }
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());

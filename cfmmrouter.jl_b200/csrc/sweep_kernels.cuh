@@ -99,7 +99,7 @@ struct ProductPools {
     return p;
   }
   __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
-                                       bool exact) const {
+                                       bool exact, bool) const {
     return product_arb(p.R.x, p.R.y, p.g, v1, v2, exact);
   }
 };
@@ -121,7 +121,8 @@ struct GeomeanPools {
     return p;
   }
   __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
-                                       bool exact) const {
+                                       bool exact, bool econ) const {
+    if (econ && !exact) return geomean_arb_econ(p.R.x, p.R.y, p.w.x, p.w.y, p.g, v1, v2);
     return geomean_arb(p.R.x, p.R.y, p.w.x, p.w.y, p.g, v1, v2, exact);
   }
 };
@@ -151,7 +152,7 @@ struct Univ3Pools {
     return p;
   }
   __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
-                                       bool) const {
+                                       bool, bool) const {
     return univ3_arb(lower + p.off, liq + p.off, p.nt, p.cp, p.cur, p.g, v1, v2);
   }
 };
@@ -175,6 +176,8 @@ __global__ void __launch_bounds__(kSweepThreads)
   // only by tools/explore.py to attribute time; the product never sets them.
   const bool exact = flags & 1;
   const bool skip_b = flags & 2, skip_a = flags & 4, skip_acc = flags & 8;
+  // bit4: economized closed forms (gradient-only sweeps; never with MAT)
+  const bool econ = !MAT && (flags & 16);
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (kSweepThreads / 32) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (kSweepThreads / 32);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      Trade t = pools.arb(pool[u], v1[u], v2[u], exact);
+      Trade t = pools.arb(pool[u], v1[u], v2[u], exact, econ);
       if (MAT && ok[u]) {
         const int64_t i = base + u * 32 + lane;
         outD[i] = make_double2(t.d1, t.d2);

@@ -180,6 +180,14 @@ def test_geomean_sweep_parity(cr, oracle, synth, m, n, exact):
     assert np.all(np.abs(D - Do)[big] <= 1e-6 * Do[big])
     # fold parity against the GPU's own per-pool trades
     check_psi(oracle, Ai, D, L, v, n, psi, acc)
+    if exact == 0:
+        # gradient-only sweep: economized one-pow form (few ulp of the reserves) ...
+        psi2, acc2 = p.sweep(v)
+        check_psi(oracle, Ai, D, L, v, n, psi2, acc2, R=R, g=g)
+        # ... and the reference operation order
+        p.set_option("gradient_math", 0)
+        psi3, acc3 = p.sweep(v)
+        check_psi(oracle, Ai, D, L, v, n, psi3, acc3)
     p.close()
 
 

@@ -72,6 +72,15 @@ def main():
         res.append(row)
         p.close()
 
+    if len(sys.argv) > 1 and sys.argv[1] == "other":
+        run("geomean 500k warm", 500_000, 10_000, "geomean", "near", iters=50)
+        run("geomean 5M econ", 5_000_000, 10_000, "geomean", "near", iters=10)
+        run("geomean 5M reference-order", 5_000_000, 10_000, "geomean", "near", iters=10, gradient_math=0)
+        run("geomean 5M exact", 5_000_000, 10_000, "geomean", "near", iters=5, exact=1)
+        run("univ3 500k warm", 500_000, 5_000, "univ3", iters=50)
+        run("univ3 500k flushed", 500_000, 5_000, "univ3", iters=20, use_flush=True)
+        run("univ3 5M", 5_000_000, 50_000, "univ3", iters=10)
+        return
     M, N = 10_000_000, 50_000
     for nu in ("near", "wide", "ones"):
         run("c5 tma", M, N, "product", nu)
