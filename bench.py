@@ -330,8 +330,8 @@ def run_ours(args):
         # ---- e2e: public C-ABI call with pinned host buffers, copies inside ----
         e2e_steps = args.e2e_steps or min(args.steps, 2000)
         h_nu = torch.from_numpy(nu_host).pin_memory()
-        h_psi = torch.zeros(n, dtype=torch.float64).pin_memory()
-        h_acc = torch.zeros(1, dtype=torch.float64).pin_memory()
+        h_out = torch.zeros(n + 1, dtype=torch.float64).pin_memory()  # [psi ; acc] contiguous
+        h_psi, h_acc = h_out[:n], h_out[n:]
         for _ in range(3):
             pools.sweep_into(h_nu.data_ptr(), h_psi.data_ptr(), h_acc.data_ptr())
         barrier()

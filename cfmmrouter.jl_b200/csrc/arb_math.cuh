@@ -232,55 +232,44 @@ __device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w
 // UniV3 -- src/cfmms.jl:251-259, 272-289, 294-313, 321-337, 339-395
 // ---------------------------------------------------------------------------
 
-struct BoundedProduct {  // src/cfmms.jl:272-278
-  double k, alpha, beta, R1, R2;
-};
+// Every tick's BoundedProduct (src/cfmms.jl:272-278, built by compute_at_tick
+// :294-313) depends only on pool state (liquidity, tick prices, current price),
+// never on ν.  It is therefore evaluated ONCE at cfmm_finalize, on the host,
+// with the same IEEE operations in the same order, and stored per tick as
+//   td[0] = k            td[1] = R_1 + α      td[2] = R_2 + β     td[3] = R_1
+//   td[4] = R_2          td[5] = k/β − (R_1+α)   (δ_max, "upper" direction)
+//   td[6] = k/α − (R_2+β)  (δ_max of the flipped pool, "lower" direction)   td[7] = pad
+// so a visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
+constexpr int kTickStride = 8;
 
-// compute_at_tick, src/cfmms.jl:294-313.  idx, current_tick are 1-based;
-// lt/lq point at this pool's first tick.
-__device__ __forceinline__ BoundedProduct univ3_tick(
-    const double* __restrict__ lt, const double* __restrict__ lq, int n_ticks,
-    double current_price, int current_tick, int idx) {
-  BoundedProduct t;
-  const double k = __ldg(lq + idx - 1);
-  const double pplus = __ldg(lt + idx - 1);                    // tick_high_price :252
-  const double pminus = (idx < n_ticks) ? __ldg(lt + idx) : 0.0;  // tick_low_price :255-259
-  t.k = k;
-  t.alpha = __dsqrt_rn(__ddiv_rn(k, pplus));
-  t.beta = __dsqrt_rn(__dmul_rn(k, pminus));
-  const double p =
-      (idx > current_tick) ? pplus : (idx < current_tick) ? pminus : current_price;
-  t.R1 = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, p)), t.alpha);
-  t.R2 = __dsub_rn(__dsqrt_rn(__dmul_rn(k, p)), t.beta);
-  return t;
-}
-
-// find_arb_pos, src/cfmms.jl:321-337
-__device__ __forceinline__ void find_arb_pos(const BoundedProduct& t,
-                                             double price, double& delta,
-                                             double& lambda) {
-  const double ra = __dadd_rn(t.R1, t.alpha);
-  const double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(t.k, price)), ra);
+// find_arb_pos (src/cfmms.jl:321-337) on a precomputed tick; `flip` selects the
+// flip_sides view (src/cfmms.jl:289).
+template <bool FLIP>
+__device__ __forceinline__ void find_arb_pos_pre(const double* __restrict__ td, double k,
+                                                 double price, double& delta, double& lambda) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(td));      // (k, R1+α)
+  const double2 b = __ldg(reinterpret_cast<const double2*>(td) + 1);  // (R2+β, R1)
+  const double ra = FLIP ? b.x : a.y;                                  // t.R_1 + t.α
+  const double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), ra);
   if (d <= 0.0) {
     delta = 0.0;
     lambda = 0.0;
     return;
   }
-  const double dmax = __dsub_rn(__ddiv_rn(t.k, t.beta), ra);
+  const double2 c = __ldg(reinterpret_cast<const double2*>(td) + 2);  // (R2, δmax_up)
+  const double dmax = FLIP ? __ldg(td + 6) : c.y;
   if (d >= dmax) {
     delta = dmax;
-    lambda = t.R2;
+    lambda = FLIP ? b.y : c.x;  // t.R_2
     return;
   }
   delta = d;
-  lambda = __dsub_rn(__dadd_rn(t.R2, t.beta), __dsqrt_rn(__dmul_rn(price, t.k)));
+  lambda = __dsub_rn(FLIP ? a.y : b.x, __dsqrt_rn(__dmul_rn(price, k)));  // (R_2+β) − sqrt(price·k)
 }
 
 // find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395
-__device__ __forceinline__ Trade univ3_arb(const double* __restrict__ lt,
-                                           const double* __restrict__ lq,
-                                           int n_ticks, double current_price,
-                                           int current_tick, double g,
+__device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks,
+                                           double current_price, int current_tick, double g,
                                            double v1, double v2) {
   Trade t;
   t.d1 = t.d2 = t.l1 = t.l2 = 0.0;
@@ -293,14 +282,14 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ lt,
     bool initial = true;
     double dsum = 0.0, lsum = 0.0;
     for (int idx = current_tick; idx <= n_ticks; ++idx) {  // get_upper_pools :316
-      const BoundedProduct pool =
-          univ3_tick(lt, lq, n_ticks, current_price, current_tick, idx);
-      if (pool.k == 0.0) {
+      const double* tk = td + (size_t)(idx - 1) * kTickStride;
+      const double k = __ldg(tk);
+      if (k == 0.0) {  // is_empty_pool: skipped, not terminal
         initial = false;
         continue;
       }
       double d, l;
-      find_arb_pos(pool, price, d, l);
+      find_arb_pos_pre<false>(tk, k, price, d, l);
       if (!initial && (d == 0.0 || l == 0.0)) break;
       dsum = __dadd_rn(dsum, d);
       lsum = __dadd_rn(lsum, l);
@@ -313,20 +302,14 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ lt,
     bool initial = true;
     double dsum = 0.0, lsum = 0.0;
     for (int idx = current_tick; idx >= 1; --idx) {  // flip_sides.(get_lower_pools) :375
-      BoundedProduct pool =
-          univ3_tick(lt, lq, n_ticks, current_price, current_tick, idx);
-      if (pool.k == 0.0) {
+      const double* tk = td + (size_t)(idx - 1) * kTickStride;
+      const double k = __ldg(tk);
+      if (k == 0.0) {
         initial = false;
         continue;
       }
-      double tmp = pool.alpha;
-      pool.alpha = pool.beta;
-      pool.beta = tmp;
-      tmp = pool.R1;
-      pool.R1 = pool.R2;
-      pool.R2 = tmp;
       double d, l;
-      find_arb_pos(pool, price, d, l);
+      find_arb_pos_pre<true>(tk, k, price, d, l);
       if (!initial && (d == 0.0 || l == 0.0)) break;
       dsum = __dadd_rn(dsum, d);
       lsum = __dadd_rn(lsum, l);

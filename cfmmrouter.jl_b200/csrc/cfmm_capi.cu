@@ -61,7 +61,7 @@ struct PoolSet {
   std::vector<int64_t> order;             // sorted position -> insertion index within type
   std::vector<int64_t> pos_of;            // lazily: insertion index -> sorted position
   DevBuf<double2> d_R, d_w, d_outD, d_outL;
-  DevBuf<double> d_gam, d_cp, d_lower, d_liq;
+  DevBuf<double> d_gam, d_cp, d_tickdata;
   DevBuf<int2> d_Ai, d_tick;
   DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
   int64_t total_ticks = 0;
@@ -73,7 +73,7 @@ struct PoolSet {
   DevBuf<int> d_tile_bucket;   // bucket of every tile
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
-    d_gam.release(); d_cp.release(); d_lower.release(); d_liq.release();
+    d_gam.release(); d_cp.release(); d_tickdata.release();
     d_Ai.release(); d_tick.release(); d_gidx.release(); d_tile_bucket.release();
   }
 };
@@ -287,27 +287,45 @@ int upload_set(cfmm_ctx* ctx, int type) {
     CU_TRY(ctx, s.d_w.upload(w));
   }
   if (type == CFMM_POOL_UNIV3) {
-    std::vector<double> cp((size_t)m), lower, liq;
+    // compute_at_tick (src/cfmms.jl:294-313) for every tick, once, on the host:
+    // IEEE sqrt / div / mul / sub in the reference's order (see arb_math.cuh)
+    std::vector<double> cp((size_t)m), td;
     std::vector<int2> tick((size_t)m);
-    lower.reserve(s.lower.size());
-    liq.reserve(s.liq.size());
+    td.reserve(s.lower.size() * cfmm::kTickStride);
+    int64_t n_ticks_total = 0;
     for (int64_t p = 0; p < m; ++p) {
       const int64_t i = s.order[(size_t)p];
       const int64_t b = s.tick_off[(size_t)i], e = s.tick_off[(size_t)i + 1];
-      cp[(size_t)p] = s.cp[(size_t)i];
+      const double price = s.cp[(size_t)i];
+      cp[(size_t)p] = price;
       // current_tick = searchsortedlast(lower_ticks, current_price; rev=true)
       // (src/cfmms.jl:235): number of leading ticks >= current_price
       int cur = 0;
-      while (b + cur < e && s.lower[(size_t)(b + cur)] >= s.cp[(size_t)i]) ++cur;
-      tick[(size_t)p] = make_int2((int)lower.size(), cur);
-      lower.insert(lower.end(), s.lower.begin() + b, s.lower.begin() + e);
-      liq.insert(liq.end(), s.liq.begin() + b, s.liq.begin() + e);
+      while (b + cur < e && s.lower[(size_t)(b + cur)] >= price) ++cur;
+      tick[(size_t)p] = make_int2((int)n_ticks_total, cur);
+      for (int64_t q = b; q < e; ++q) {
+        const int idx = (int)(q - b) + 1;  // 1-based
+        volatile double k = s.liq[(size_t)q];
+        volatile double pplus = s.lower[(size_t)q];                      // tick_high_price :252
+        volatile double pminus = (q + 1 < e) ? s.lower[(size_t)q + 1] : 0.0;  // tick_low_price :255-259
+        volatile double alpha = std::sqrt(k / pplus);
+        volatile double beta = std::sqrt(k * pminus);
+        volatile double pp = idx > cur ? pplus : (idx < cur ? pminus : price);
+        volatile double R1 = std::sqrt(k / pp) - alpha;
+        volatile double R2 = std::sqrt(k * pp) - beta;
+        volatile double ra = R1 + alpha;
+        volatile double rb = R2 + beta;
+        volatile double dmax_up = k / beta - ra;
+        volatile double dmax_dn = k / alpha - rb;
+        const double rec[cfmm::kTickStride] = {k, ra, rb, R1, R2, dmax_up, dmax_dn, 0.0};
+        td.insert(td.end(), rec, rec + cfmm::kTickStride);
+      }
+      n_ticks_total += e - b;
     }
-    s.total_ticks = (int64_t)lower.size();
+    s.total_ticks = n_ticks_total;
     CU_TRY(ctx, s.d_cp.upload(cp));
     CU_TRY(ctx, s.d_tick.upload(tick));
-    CU_TRY(ctx, s.d_lower.upload(lower));
-    CU_TRY(ctx, s.d_liq.upload(liq));
+    CU_TRY(ctx, s.d_tickdata.upload(td));
   }
   // host staging is no longer needed (order is kept for update_reserves)
   std::vector<double>().swap(s.R);
@@ -483,7 +501,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     constexpr int PT = CFMM_POOL_UNIV3;
     if (s.m > 0) {
       cfmm::Univ3Pools p{s.d_cp.p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
-                         s.d_lower.p, s.d_liq.p, s.m_padded, (int)s.total_ticks};
+                         s.d_tickdata.p, s.m_padded, (int)s.total_ticks};
       if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }
   }
@@ -703,6 +721,12 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   const double* res = nullptr;
   rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, materialize != 0, st, &res);
   if (rc != CFMM_OK) return rc;
+  if (acc_out == psi_out + ctx->n_tokens) {
+    // caller keeps [psi ; acc] contiguous: one D2H copy
+    CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb + sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return CFMM_OK;
+  }
   CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, res + ctx->n_tokens,
                               sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -132,8 +132,7 @@ struct Univ3Pools {
   const double* gam;
   const int2* Ai;
   const int2* tick;       // (tick_off, current_tick 1-based)   -> 32 B header
-  const double* lower;    // CSR, 8 B/tick
-  const double* liq;      // CSR, 8 B/tick
+  const double* tickdata; // CSR, kTickStride doubles per tick (precomputed BoundedProduct, see arb_math.cuh)
   int64_t m;
   int total_ticks;
   struct Pool {
@@ -153,7 +152,7 @@ struct Univ3Pools {
   }
   __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
                                        bool, bool) const {
-    return univ3_arb(lower + p.off, liq + p.off, p.nt, p.cp, p.cur, p.g, v1, v2);
+    return univ3_arb(tickdata + (size_t)p.off * kTickStride, p.nt, p.cp, p.cur, p.g, v1, v2);
   }
 };
 

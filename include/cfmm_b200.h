@@ -107,7 +107,8 @@ int64_t cfmm_num_tokens(const cfmm_ctx *ctx);
  * route!, router.jl:107) for cfmm_get_trades.  Blocking: results are valid on
  * return.  When the context belongs to a multi-GPU group (cfmm_comm_attach),
  * psi/acc are the sums over all ranks' shards and every rank must call it.
- * Buffers from cfmm_host_alloc (pinned) avoid a staging copy. */
+ * Buffers from cfmm_host_alloc (pinned) avoid a staging copy; if acc_out ==
+ * psi_out + n_tokens (one contiguous [psi ; acc] buffer) a single copy is used. */
 int cfmm_sweep(cfmm_ctx *ctx, const double *v, double *psi_out,
                double *acc_out, int materialize);
 
