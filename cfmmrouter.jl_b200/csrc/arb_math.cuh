@@ -242,32 +242,9 @@ __device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w
 // so a visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
 constexpr int kTickStride = 8;
 
-// find_arb_pos (src/cfmms.jl:321-337) on a precomputed tick; `flip` selects the
-// flip_sides view (src/cfmms.jl:289).
-template <bool FLIP>
-__device__ __forceinline__ void find_arb_pos_pre(const double* __restrict__ td, double k,
-                                                 double price, double& delta, double& lambda) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(td));      // (k, R1+α)
-  const double2 b = __ldg(reinterpret_cast<const double2*>(td) + 1);  // (R2+β, R1)
-  const double ra = FLIP ? b.x : a.y;                                  // t.R_1 + t.α
-  const double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), ra);
-  if (d <= 0.0) {
-    delta = 0.0;
-    lambda = 0.0;
-    return;
-  }
-  const double2 c = __ldg(reinterpret_cast<const double2*>(td) + 2);  // (R2, δmax_up)
-  const double dmax = FLIP ? __ldg(td + 6) : c.y;
-  if (d >= dmax) {
-    delta = dmax;
-    lambda = FLIP ? b.y : c.x;  // t.R_2
-    return;
-  }
-  delta = d;
-  lambda = __dsub_rn(FLIP ? a.y : b.x, __dsqrt_rn(__dmul_rn(price, k)));  // (R_2+β) − sqrt(price·k)
-}
-
-// find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395
+// find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395.  Both walk directions
+// share one loop (the direction is data: index step and field selection), so a
+// warp whose lanes walk in different directions does not execute two loops.
 __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks,
                                            double current_price, int current_tick, double g,
                                            double v1, double v2) {
@@ -277,45 +254,49 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const double lo = __dmul_rn(g, current_price);
   // no-arb interval :347
   if (lo <= p && p <= __ddiv_rn(current_price, g)) return t;
-  if (p < lo) {
-    const double price = __ddiv_rn(p, g);
-    bool initial = true;
-    double dsum = 0.0, lsum = 0.0;
-    for (int idx = current_tick; idx <= n_ticks; ++idx) {  // get_upper_pools :316
-      const double* tk = td + (size_t)(idx - 1) * kTickStride;
-      const double k = __ldg(tk);
-      if (k == 0.0) {  // is_empty_pool: skipped, not terminal
-        initial = false;
-        continue;
-      }
-      double d, l;
-      find_arb_pos_pre<false>(tk, k, price, d, l);
-      if (!initial && (d == 0.0 || l == 0.0)) break;
-      dsum = __dadd_rn(dsum, d);
-      lsum = __dadd_rn(lsum, l);
+  const bool up = p < lo;  // :351 "upper pools" (towards lower prices); else :373 lower pools, flipped
+  // price = p/γ (:359)  or  1/(γ·p) (:381)
+  const double price = __ddiv_rn(up ? p : 1.0, up ? g : __dmul_rn(g, p));
+  const int step = up ? 1 : -1;
+  const int last = up ? n_ticks : 1;
+  bool initial = true;
+  double dsum = 0.0, lsum = 0.0;
+  for (int idx = current_tick; up ? (idx <= last) : (idx >= last); idx += step) {
+    const double* tk = td + (size_t)(idx - 1) * kTickStride;
+    const double2 a = __ldg(reinterpret_cast<const double2*>(tk));      // (k, R1+α)
+    const double k = a.x;
+    if (k == 0.0) {  // is_empty_pool: skipped, not terminal (:354-357, :376-379)
       initial = false;
+      continue;
     }
-    t.d1 = __ddiv_rn(dsum, g);
+    // find_arb_pos (src/cfmms.jl:321-337) on the (flipped, :289) precomputed tick
+    const double2 b = __ldg(reinterpret_cast<const double2*>(tk) + 1);  // (R2+β, R1)
+    const double ra = up ? a.y : b.x;                                   // t.R_1 + t.α
+    double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), ra), l;
+    if (d <= 0.0) {
+      d = 0.0;
+      l = 0.0;
+    } else {
+      const double2 c = __ldg(reinterpret_cast<const double2*>(tk) + 2);  // (R2, δmax_up)
+      const double dmax = up ? c.y : __ldg(tk + 6);
+      if (d >= dmax) {
+        d = dmax;
+        l = up ? c.x : b.y;  // t.R_2
+      } else {
+        l = __dsub_rn(up ? b.x : a.y, __dsqrt_rn(__dmul_rn(price, k)));  // (R_2+β) − sqrt(price·k)
+      }
+    }
+    if (!initial && (d == 0.0 || l == 0.0)) break;  // :362, :384
+    dsum = __dadd_rn(dsum, d);
+    lsum = __dadd_rn(lsum, l);
+    initial = false;
+  }
+  const double dn = __ddiv_rn(dsum, g);  // pre-fee tendered amount :371, :391
+  if (up) {
+    t.d1 = dn;
     t.l2 = lsum;
   } else {
-    const double price = __ddiv_rn(1.0, __dmul_rn(g, p));
-    bool initial = true;
-    double dsum = 0.0, lsum = 0.0;
-    for (int idx = current_tick; idx >= 1; --idx) {  // flip_sides.(get_lower_pools) :375
-      const double* tk = td + (size_t)(idx - 1) * kTickStride;
-      const double k = __ldg(tk);
-      if (k == 0.0) {
-        initial = false;
-        continue;
-      }
-      double d, l;
-      find_arb_pos_pre<true>(tk, k, price, d, l);
-      if (!initial && (d == 0.0 || l == 0.0)) break;
-      dsum = __dadd_rn(dsum, d);
-      lsum = __dadd_rn(lsum, l);
-      initial = false;
-    }
-    t.d2 = __ddiv_rn(dsum, g);
+    t.d2 = dn;
     t.l1 = lsum;
   }
   return t;

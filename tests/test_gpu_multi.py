@@ -127,14 +127,18 @@ def _worker(rank, world, port, out_dir):
 @pytest.mark.timeout(600)
 def test_one_process_per_gpu_ipc_exchange(cr, oracle, tmp_path):
     import torch.multiprocessing as mp
-    world = 2
+    world = min(_ngpu(), 8)  # every visible GPU: 2, 4 or 8 ranks
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     ref, accref, tol, atol = _reference(oracle)
     outs = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
-    assert np.array_equal(outs[0]["psi"], outs[1]["psi"]) and np.array_equal(outs[0]["acc"], outs[1]["acc"])
+    for o in outs[1:]:  # bitwise-identical reduced vectors on every rank
+        assert np.array_equal(outs[0]["psi"], o["psi"]) and np.array_equal(outs[0]["acc"], o["acc"])
     for k in range(4):
         assert np.all(np.abs(outs[0]["psi"][k] - ref) <= tol)
         assert abs(outs[0]["acc"][k] - accref) <= atol
-    ra, rb = np.load(tmp_path / "route0.npz"), np.load(tmp_path / "route1.npz")
-    assert np.array_equal(ra["v"], rb["v"]) and np.array_equal(ra["D"], rb["D"]) and np.array_equal(ra["L"], rb["L"])
+    routes = [np.load(tmp_path / f"route{k}.npz") for k in range(world)]
+    for r in routes[1:]:
+        assert np.array_equal(routes[0]["v"], r["v"]) and np.array_equal(routes[0]["D"], r["D"]) \
+            and np.array_equal(routes[0]["L"], r["L"])
+    ra = routes[0]
     assert ra["D"].shape == (200, 2) and np.all(ra["D"] >= 0) and np.any(ra["D"] > 0)
