@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--workload", default="config5_10M_product_50k_tokens", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer")
+    ap.add_argument("--two-shot", type=int, default=-1, help="peer exchange protocol: -1 auto (two-shot for N>2), 0, 1")
     ap.add_argument("--nu", choices=["near", "wide", "ones"], default="near")
     ap.add_argument("--exact", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -274,6 +275,8 @@ def run_ours(args):
                 if rank == 0:
                     print(f"[bench] peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
                 exchange = "nccl"
+            if exchange == "peer" and args.two_shot >= 0:
+                pools.set_option("exchange_two_shot", args.two_shot)
             flag = torch.tensor([1 if exchange == "peer" else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() == 0 and exchange == "peer":

@@ -837,6 +837,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "exchange_two_shot")) {
+    ctx->comm.force_mode((int)value);
   } else if (!strcmp(key, "sweep_events")) {
     ctx->sweep_events = value != 0;
   } else if (!strcmp(key, "a_red_per_thread")) {

@@ -52,6 +52,8 @@ struct ExchangeView {
   ulonglong2* recv_local;             // this rank's receive buffer
   ulonglong2* recv_peer[kMaxPeers];   // peer-mapped receive buffers (own entry unused)
   int world, rank;
+  int64_t slice;                      // two-shot: tokens owned per rank = ceil(len / world)
+  int64_t gather_off;                 // two-shot: packet offset of the gathered-result area
 };
 
 __device__ __forceinline__ void st_packet(ulonglong2* p, unsigned long long a, unsigned long long b) {
@@ -97,16 +99,70 @@ __global__ void __launch_bounds__(kExchangeThreads)
   }
 }
 
+// Two-shot variant for world > 2 (reduce-scatter + all-gather, both as LL
+// pushes): element j is owned by rank j / slice.  A non-owner pushes its partial
+// to the owner's contribution area and then polls its own gathered-result area;
+// the owner polls the world-1 contributions, sums in rank order, writes the
+// result and pushes it to every peer's gathered-result area.  Per rank
+// 2·(W−1)/W·len packets cross NVLink instead of (W−1)·len, at the price of a
+// second hop.  Every rank receives the owner's bits, so results are identical
+// everywhere by construction.  No thread waits on another thread of its own
+// rank, so the grid need not be co-resident.
+__global__ void __launch_bounds__(kExchangeThreads)
+    peer_allreduce_twoshot_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
+                                  unsigned int epoch) {
+  const int par = (int)(epoch & 1u);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const unsigned long long tag = (unsigned long long)epoch;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
+    const int owner = (int)(j / x.slice);
+    const int64_t i = j - (int64_t)owner * x.slice;
+    const double mine = src[j];
+    if (owner != x.rank) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+      st_packet(x.recv_peer[owner] + ((int64_t)(x.rank * 2 + par) * x.slice + i),
+                ((bits >> 32) << 32) | tag, ((bits & 0xffffffffull) << 32) | tag);
+      const ulonglong2* q = x.recv_local + x.gather_off + (int64_t)par * len + j;
+      ulonglong2 v = ld_packet(q);
+      while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+      dst[j] = __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
+    } else {
+      double s = 0.0;
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p >= x.world) continue;
+        if (p == x.rank) {
+          s += mine;
+          continue;
+        }
+        const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * x.slice + i);
+        ulonglong2 v = ld_packet(q);
+        while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+        s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
+      }
+      dst[j] = s;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+      const unsigned long long w0 = ((bits >> 32) << 32) | tag, w1 = ((bits & 0xffffffffull) << 32) | tag;
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < x.world && p != x.rank)
+          st_packet(x.recv_peer[p] + x.gather_off + (int64_t)par * len + j, w0, w1);
+    }
+  }
+}
+
 class PeerExchange {
  public:
   bool attached() const { return attached_ && world_ > 1; }
   const std::string& error() const { return err_; }
   int launches_per_reduce() const { return 1; }
+  void force_mode(int two_shot) { two_shot_ = two_shot != 0 && world_ > 1; }
 
   bool export_handle(int64_t len, PeerHandle* out) {
     if (!base_) {
       len_ = len;
-      bytes_ = (size_t)kMaxPeers * 2 * (size_t)len * sizeof(ulonglong2);
+      // kMaxPeers contribution areas x 2 parities, plus 2 gathered-result areas (two-shot)
+      bytes_ = (size_t)(kMaxPeers + 1) * 2 * (size_t)len * sizeof(ulonglong2);
       if (!ok(cudaMalloc(&base_, bytes_), "cudaMalloc(exchange)")) return false;
       if (!ok(cudaMemset(base_, 0, bytes_), "cudaMemset(exchange)")) return false;
     }
@@ -140,6 +196,9 @@ class PeerExchange {
     view_.world = world;
     view_.rank = rank;
     view_.recv_local = (ulonglong2*)base_;
+    view_.slice = (len_ + world - 1) / world;
+    view_.gather_off = (int64_t)kMaxPeers * 2 * len_;
+    two_shot_ = world > 2;
     for (int p = 0; p < world; ++p) {
       PeerHandle h;
       memcpy(&h, handles + (size_t)p * stride, sizeof(h));
@@ -183,7 +242,10 @@ class PeerExchange {
     }
     ++epoch_;
     if (epoch_ == 0) epoch_ = 2;  // 0 is the value of untouched memory; keep parity moving
-    peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
+    if (two_shot_)
+      peer_allreduce_twoshot_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
+    else
+      peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
     return ok(cudaGetLastError(), "peer_allreduce_kernel launch");
   }
 
@@ -212,6 +274,7 @@ class PeerExchange {
   int world_ = 1, rank_ = 0, grid_ = 64;
   unsigned int epoch_ = 0;
   bool attached_ = false;
+  bool two_shot_ = false;
   ExchangeView view_;
   std::string err_;
 };

@@ -77,7 +77,10 @@ def test_two_contexts_one_process_peer_exchange(cr, oracle):
     for r, (p, _) in enumerate(pools):
         p._chk(p._lib.cfmm_comm_attach(p._ctx, world, r, handles))
     ref, accref, tol, atol = _reference(oracle)
-    for sweep in range(3):  # several epochs: slot double-buffering
+    for sweep in range(7):  # several epochs: slot double-buffering; both protocols
+        if sweep == 3:  # switch to the two-shot (reduce-scatter + gather) protocol
+            for p, _ in pools:
+                p.set_option("exchange_two_shot", 1)
         out = [None] * world
 
         def run(r):
@@ -107,7 +110,9 @@ def _worker(rank, world, port, out_dir):
     try:
         p, v = _shard(cr, rank, world)
         p.attach_group(dist.group.WORLD)  # cudaIpc handles over torch.distributed
-        res = [p.sweep(v) for _ in range(4)]
+        res = [p.sweep(v) for _ in range(2)]
+        p.set_option("exchange_two_shot", 1 if world == 2 else 0)  # the protocol that is not the default here
+        res += [p.sweep(v) for _ in range(2)]
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=np.stack([r[0] for r in res]),
                  acc=np.array([r[1] for r in res]))
         # the Router-level path: every rank ends with the same route! result
