@@ -103,6 +103,10 @@ struct cfmm_ctx {
   unsigned long long epoch = 0;  // sweeps enqueued so far
   DevBuf<double> d_accum[2];     // ping-pong [Ψ; acc] accumulators, zeroed one sweep ahead in-kernel
   double* zero_pending = nullptr; // accumulator the first kernel of the current sweep must zero
+  DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
+  unsigned long long grid_done_target = 0;
+  int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
+  cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived
   int64_t launches = 0;
   std::string err;
@@ -427,11 +431,18 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
   if (grid > n_tiles) grid = n_tiles;
+  cfmm::FusedExchange fx = ctx->fx_pending;
+  if (fx.mode != 0) {
+    ctx->grid_done_target += (unsigned long long)grid;
+    fx.target = ctx->grid_done_target;
+    fx.grid_done = ctx->d_grid_done.p;
+    ctx->fx_pending.mode = 0;  // consumed
+  }
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
       (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0,
-      ctx->exact | (ctx->a_red_per_thread ? 0 : 16));
+      ctx->exact | (ctx->a_red_per_thread ? 0 : 16), fx);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;
@@ -475,6 +486,19 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
   double* d_psi = ctx->d_accum[ctx->epoch & 1].p;
   ctx->zero_pending = ctx->d_accum[(ctx->epoch + 1) & 1].p;
   const size_t acc_bytes = (size_t)(ctx->n_tokens + 1) * sizeof(double);
+  // Fused compute+collective: when the TMA ProductTwoCoin kernel is the only
+  // kernel of this sweep, it runs the peer exchange in its own tail.
+  bool fused = false;
+  {
+    const PoolSet& ps = ctx->sets[CFMM_POOL_PRODUCT];
+    if (ctx->comm.attached() && ctx->fused_exchange && !mat && ps.m > 0 && ps.tma_ok && ctx->use_tma &&
+        ctx->debug_skip == 0 && ctx->sets[CFMM_POOL_GEOMEAN].m == 0 && ctx->sets[CFMM_POOL_UNIV3].m == 0) {
+      fused = true;
+      ctx->fx_pending.view = ctx->comm.view();
+      ctx->fx_pending.dst = d_dst ? d_dst : d_psi;
+      ctx->fx_pending.epoch = ctx->comm.begin_fused(&ctx->fx_pending.mode);
+    }
+  }
   int rc;
   {
     PoolSet& s = ctx->sets[CFMM_POOL_PRODUCT];
@@ -509,7 +533,9 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     CU_TRY(ctx, cudaMemsetAsync(take_zero_pending(ctx), 0, acc_bytes, st));
   }
   const double* result = d_psi;
-  if (ctx->comm.attached()) {
+  if (fused) {
+    result = d_dst ? d_dst : d_psi;
+  } else if (ctx->comm.attached()) {
     ProfScope prof(ctx, 3, st);
     double* dst = d_dst ? d_dst : d_psi;
     if (!ctx->comm.all_reduce(d_psi, dst, ctx->n_tokens + 1, st))
@@ -583,6 +609,9 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   CREATE_TRY(cudaEventCreate(&ctx->ev1));
   CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
   CREATE_TRY(ctx->d_psi.alloc((size_t)n_tokens + 1));
+  CREATE_TRY(ctx->d_grid_done.alloc(1));
+  CREATE_TRY(cudaMemset(ctx->d_grid_done.p, 0, sizeof(unsigned long long)));
+  memset(&ctx->fx_pending, 0, sizeof(ctx->fx_pending));
   for (auto& a : ctx->d_accum) {
     CREATE_TRY(a.alloc((size_t)n_tokens + 1));
     CREATE_TRY(cudaMemset(a.p, 0, ((size_t)n_tokens + 1) * sizeof(double)));
@@ -603,6 +632,7 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_psi.release();
+  ctx->d_grid_done.release();
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -837,6 +867,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "fused_exchange")) {
+    ctx->fused_exchange = value != 0;
   } else if (!strcmp(key, "exchange_two_shot")) {
     ctx->comm.force_mode((int)value);
   } else if (!strcmp(key, "sweep_events")) {

@@ -65,14 +65,14 @@ __device__ __forceinline__ ulonglong2 ld_packet(const ulonglong2* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kExchangeThreads)
-    peer_allreduce_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
-                          unsigned int epoch) {
+// one-shot body for elements first, first+stride, ... (callable from any kernel)
+__device__ __forceinline__ void peer_allreduce_oneshot_body(const ExchangeView& x, const double* src,
+                                                            double* dst, int64_t len, unsigned int epoch,
+                                                            int64_t first, int64_t stride) {
   const int par = (int)(epoch & 1u);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const unsigned long long tag = (unsigned long long)epoch;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
-    const double mine = src[j];
+  for (int64_t j = first; j < len; j += stride) {
+    const double mine = __ldcg(src + j);
     const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
     const unsigned long long w0 = ((bits >> 32) << 32) | tag;         // {hi32 | epoch}
     const unsigned long long w1 = ((bits & 0xffffffffull) << 32) | tag;  // {lo32 | epoch}
@@ -99,6 +99,14 @@ __global__ void __launch_bounds__(kExchangeThreads)
   }
 }
 
+__global__ void __launch_bounds__(kExchangeThreads)
+    peer_allreduce_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
+                          unsigned int epoch) {
+  peer_allreduce_oneshot_body(x, src, dst, len, epoch,
+                              (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                              (int64_t)gridDim.x * blockDim.x);
+}
+
 // Two-shot variant for world > 2 (reduce-scatter + all-gather, both as LL
 // pushes): element j is owned by rank j / slice.  A non-owner pushes its partial
 // to the owner's contribution area and then polls its own gathered-result area;
@@ -108,16 +116,15 @@ __global__ void __launch_bounds__(kExchangeThreads)
 // second hop.  Every rank receives the owner's bits, so results are identical
 // everywhere by construction.  No thread waits on another thread of its own
 // rank, so the grid need not be co-resident.
-__global__ void __launch_bounds__(kExchangeThreads)
-    peer_allreduce_twoshot_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
-                                  unsigned int epoch) {
+__device__ __forceinline__ void peer_allreduce_twoshot_body(const ExchangeView& x, const double* src,
+                                                            double* dst, int64_t len, unsigned int epoch,
+                                                            int64_t first, int64_t stride) {
   const int par = (int)(epoch & 1u);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const unsigned long long tag = (unsigned long long)epoch;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += stride) {
+  for (int64_t j = first; j < len; j += stride) {
     const int owner = (int)(j / x.slice);
     const int64_t i = j - (int64_t)owner * x.slice;
-    const double mine = src[j];
+    const double mine = __ldcg(src + j);
     if (owner != x.rank) {
       const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
       st_packet(x.recv_peer[owner] + ((int64_t)(x.rank * 2 + par) * x.slice + i),
@@ -151,12 +158,38 @@ __global__ void __launch_bounds__(kExchangeThreads)
   }
 }
 
+__global__ void __launch_bounds__(kExchangeThreads)
+    peer_allreduce_twoshot_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
+                                  unsigned int epoch) {
+  peer_allreduce_twoshot_body(x, src, dst, len, epoch,
+                              (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                              (int64_t)gridDim.x * blockDim.x);
+}
+
+// What a sweep kernel needs to run the exchange in its own tail.
+struct FusedExchange {
+  ExchangeView view;
+  double* dst;                     // where the reduced [Ψ; acc] goes (may equal the accumulator)
+  unsigned long long* grid_done;   // device counter: CTAs that finished accumulating, all sweeps
+  unsigned long long target;       // value grid_done reaches when every CTA of THIS sweep is done
+  unsigned int epoch;
+  int mode;                        // 0 = off, 1 = one-shot, 2 = two-shot
+};
+
 class PeerExchange {
  public:
   bool attached() const { return attached_ && world_ > 1; }
   const std::string& error() const { return err_; }
   int launches_per_reduce() const { return 1; }
   void force_mode(int two_shot) { two_shot_ = two_shot != 0 && world_ > 1; }
+  // fused use: the sweep kernel itself runs the exchange body; returns the epoch to tag with
+  unsigned int begin_fused(int* mode) {
+    ++epoch_;
+    if (epoch_ == 0) epoch_ = 2;
+    *mode = two_shot_ ? 2 : 1;
+    return epoch_;
+  }
+  const ExchangeView& view() const { return view_; }
 
   bool export_handle(int64_t len, PeerHandle* out) {
     if (!base_) {

@@ -49,6 +49,19 @@ def _reference(oracle):
     return Gx.astype(np.float64), float(accx), tol, float(np.sum(tol * v))
 
 
+def _shard_product_only(cr, rank, world):
+    """Product-only shard: the sweep is ONE kernel (TMA sweep + fused exchange)."""
+    from cfmmrouter_b200 import synth
+    n = 9_000
+    R, g, Ai = synth.product_pools(400_003, n, seed=13)
+    v = synth.dual_prices(n, "near")
+    lo, hi = cr.shard_range(len(g), world, rank)
+    p = cr.DevicePools(n, device=rank)
+    p.add_product(R[lo:hi], g[lo:hi], Ai[lo:hi])
+    p.finalize()
+    return p, v, (R, g, Ai, n)
+
+
 def _shard(cr, rank, world):
     n, (R, g, Ai), (Rg, gg, Ag, wg), v = _workload()
     lo, hi = cr.shard_range(len(g), world, rank)
@@ -115,6 +128,20 @@ def _worker(rank, world, port, out_dir):
         res += [p.sweep(v) for _ in range(2)]
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=np.stack([r[0] for r in res]),
                  acc=np.array([r[1] for r in res]))
+        # product-only pool set: fused compute+collective kernel (and, for contrast, the unfused path)
+        q, vq, _ = _shard_product_only(cr, rank, world)
+        q.attach_group(dist.group.WORLD)
+        l0 = q.launch_count
+        fres = [q.sweep(vq) for _ in range(3)]
+        fused_launches = q.launch_count - l0
+        q.set_option("fused_exchange", 0)
+        fres += [q.sweep(vq) for _ in range(2)]
+        q.set_option("fused_exchange", 1)
+        q.set_option("exchange_two_shot", 1 if world == 2 else 0)
+        fres += [q.sweep(vq) for _ in range(2)]
+        np.savez(os.path.join(out_dir, f"fused{rank}.npz"), psi=np.stack([r[0] for r in fres]),
+                 acc=np.array([r[1] for r in fres]), launches=fused_launches)
+        q.close()
         # the Router-level path: every rank ends with the same route! result
         rng = np.random.default_rng(7)
         pools = [cr.ProductTwoCoin(1000 * rng.random(2) + 1, 0.997, rng.choice(np.arange(1, 9), 2, replace=False))
@@ -141,6 +168,24 @@ def test_one_process_per_gpu_ipc_exchange(cr, oracle, tmp_path):
     for k in range(4):
         assert np.all(np.abs(outs[0]["psi"][k] - ref) <= tol)
         assert abs(outs[0]["acc"][k] - accref) <= atol
+    # fused path: one launch per sweep, same bits on every rank, right answer
+    from cfmmrouter_b200 import synth
+    fo = [np.load(tmp_path / f"fused{k}.npz") for k in range(world)]
+    assert int(fo[0]["launches"]) == 3  # 3 sweeps -> 3 kernels: no separate exchange launch
+    for o in fo[1:]:
+        assert np.array_equal(fo[0]["psi"], o["psi"]) and np.array_equal(fo[0]["acc"], o["acc"])
+    n = 9_000
+    R, g, Ai = synth.product_pools(400_003, n, seed=13)
+    vq = synth.dual_prices(n, "near")
+    Do, Lo = oracle.sweep_product(R, g, Ai, vq, threads=8)
+    accx, Gx, absG = oracle.fold_compensated(Ai, Do, Lo, vq, n)
+    slack = np.zeros(n)
+    w = 32 * np.finfo(float).eps * (R[:, 0] + R[:, 1]) / g
+    np.add.at(slack, Ai[:, 0] - 1, w)
+    np.add.at(slack, Ai[:, 1] - 1, w)
+    for k in range(fo[0]["psi"].shape[0]):
+        assert np.all(np.abs(fo[0]["psi"][k] - Gx.astype(np.float64)) <= 1e-12 * absG + slack + 1e-300)
+        assert abs(fo[0]["acc"][k] - float(accx)) <= 1e-12 * float(np.sum(absG * vq)) + float(np.sum(slack * vq))
     routes = [np.load(tmp_path / f"route{k}.npz") for k in range(world)]
     for r in routes[1:]:
         assert np.array_equal(routes[0]["v"], r["v"]) and np.array_equal(routes[0]["D"], r["D"]) \
