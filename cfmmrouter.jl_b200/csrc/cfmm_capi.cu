@@ -97,6 +97,7 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
+  int b_red_pools = 0;       // how many of a thread's L pools send Ψ[b] by global RED instead of the shared slice
   int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
   int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
@@ -442,7 +443,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
       (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0,
-      ctx->exact | (ctx->a_red_per_thread ? 0 : 16), fx);
+      ctx->exact | (ctx->a_red_per_thread ? 0 : 16) | (ctx->b_red_pools << 8), fx);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;
@@ -867,6 +868,9 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "b_red_pools")) {
+    if (value < 0 || value > 7) return fail(ctx, CFMM_ERR_INVALID, "b_red_pools out of range");
+    ctx->b_red_pools = (int)value;
   } else if (!strcmp(key, "fused_exchange")) {
     ctx->fused_exchange = value != 0;
   } else if (!strcmp(key, "exchange_two_shot")) {
