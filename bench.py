@@ -196,7 +196,12 @@ def run_reference(args):
     threads = o.max_threads()
     m, n, kind = WORKLOADS[args.workload]
     # bound the whole run to ~2 minutes of CPU time: pools per step from a probe
+    # all host threads, unless half of them (one per physical core) is faster on this box
     probe_rate, _, _ = cpu_faithful_rate(args.workload, 200_000, 2, threads)
+    if threads >= 4:
+        half_rate, _, _ = cpu_faithful_rate(args.workload, 200_000, 2, threads // 2)
+        if half_rate > probe_rate:
+            threads, probe_rate = threads // 2, half_rate
     budget = 120.0 / max(1, args.steps + args.warmup)
     sample = int(max(10_000, min(m, 2_000_000, probe_rate * budget)))
     from cfmmrouter_b200 import synth
@@ -371,7 +376,7 @@ def run_ours(args):
         # dominant kernel = the one with the most event-timed device time
         dom = max((0, 1, 2), key=lambda t: prof[t][0])
         dom_ms, dom_cnt = prof[dom]
-        dom_name = {0: "sweep_kernel<ProductPools>", 1: "sweep_kernel<GeomeanPools>",
+        dom_name = {0: "product_sweep_tma (ProductTwoCoin gradient sweep)", 1: "sweep_kernel<GeomeanPools>",
                     2: "sweep_kernel<Univ3Pools>"}[dom]
         kind = WORKLOADS[args.workload][2]
         if kind == "mixed":
