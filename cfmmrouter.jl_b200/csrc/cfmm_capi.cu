@@ -71,6 +71,7 @@ struct PoolSet {
   int tma_variant = 0;         // tile shape the layout was built for
   int nb = 0;                  // bucket width in tokens
   DevBuf<int> d_tile_bucket;   // bucket of every tile
+  std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
@@ -97,6 +98,7 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
+  int orient_by_degree = 1;  // ProductTwoCoin: store each pool with its higher-degree token first (fixed at finalize)
   int b_red_pools = 0;       // how many of a thread's L pools send Ψ[b] by global RED instead of the shared slice
   int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
   int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
@@ -199,20 +201,46 @@ constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants
 
 inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
 
-// stable counting sort of pools by first token (0-based key = Ai[2i]-1)
-void token_sort(const PoolSet& s, int64_t n_tokens, std::vector<int64_t>& order) {
+// stable counting sort of pools by first token (0-based keys oa[i])
+void token_sort(const std::vector<int>& oa, int64_t n_tokens, std::vector<int64_t>& order) {
+  const int64_t m = (int64_t)oa.size();
   std::vector<int64_t> head((size_t)n_tokens + 1, 0);
-  for (int64_t i = 0; i < s.m; ++i) head[(size_t)s.Ai[2 * i]]++;  // key+1
+  for (int64_t i = 0; i < m; ++i) head[(size_t)oa[(size_t)i] + 1]++;
   for (int64_t t = 0; t < n_tokens; ++t) head[(size_t)t + 1] += head[(size_t)t];
-  order.assign((size_t)s.m, 0);
-  for (int64_t i = 0; i < s.m; ++i) order[(size_t)head[(size_t)s.Ai[2 * i] - 1]++] = i;
+  order.assign((size_t)m, 0);
+  for (int64_t i = 0; i < m; ++i) order[(size_t)head[(size_t)oa[(size_t)i]]++] = i;
 }
 
 int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
   if (s.m == 0) return CFMM_OK;
-  token_sort(s, ctx->n_tokens, s.order);
   const int64_t m = s.m;
+  // Device orientation of each pool: (oa, ob) 0-based.  ProductTwoCoin is exactly
+  // symmetric under exchanging its two tokens (k = R1·R2 commutes; every closed
+  // form of one side is the other side's with the roles swapped), so each pool
+  // is stored with its HIGHER-DEGREE token first: hub tokens of a skewed market
+  // graph then sit on the run side (register accumulation, warp-uniform ν
+  // loads) instead of hammering one shared-memory slot with fp64 CAS adds.
+  std::vector<int> oa((size_t)m), ob((size_t)m);
+  s.swapped.assign((size_t)m, 0);
+  {
+    std::vector<int64_t> deg;
+    if (type == CFMM_POOL_PRODUCT && ctx->orient_by_degree) {
+      deg.assign((size_t)ctx->n_tokens, 0);
+      for (int64_t i = 0; i < m; ++i) {
+        deg[(size_t)s.Ai[2 * i] - 1]++;
+        deg[(size_t)s.Ai[2 * i + 1] - 1]++;
+      }
+    }
+    for (int64_t i = 0; i < m; ++i) {
+      const int a = (int)(s.Ai[2 * i] - 1), b = (int)(s.Ai[2 * i + 1] - 1);
+      const bool sw = !deg.empty() && deg[(size_t)b] > deg[(size_t)a];
+      s.swapped[(size_t)i] = sw;
+      oa[(size_t)i] = sw ? b : a;
+      ob[(size_t)i] = sw ? a : b;
+    }
+  }
+  token_sort(oa, ctx->n_tokens, s.order);
   s.m_padded = m;
   s.tma_ok = false;
   std::vector<int> tile_bucket;
@@ -225,7 +253,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
     const int64_t B = (n + tv.nbmax - 1) / tv.nbmax;
     const int64_t nb = (n + B - 1) / B;
     std::vector<int64_t> cnt((size_t)B + 1, 0);
-    for (int64_t i = 0; i < m; ++i) cnt[(size_t)((s.Ai[2 * i + 1] - 1) / nb) + 1]++;
+    for (int64_t i = 0; i < m; ++i) cnt[(size_t)(ob[(size_t)i] / nb) + 1]++;
     int64_t padded = 0;
     for (int64_t k = 0; k < B; ++k) padded += (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
     if (padded <= 2 * m + 8 * tile) {  // otherwise too sparse per bucket: first-generation kernel
@@ -235,7 +263,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
       std::vector<int64_t> order((size_t)padded, -1), fill(start.begin(), start.end() - 1);
       for (int64_t p = 0; p < m; ++p) {  // stable: keeps the a-order inside a bucket
         const int64_t i = s.order[(size_t)p];
-        order[(size_t)fill[(size_t)((s.Ai[2 * i + 1] - 1) / nb)]++] = i;
+        order[(size_t)fill[(size_t)(ob[(size_t)i] / nb)]++] = i;
       }
       s.order.swap(order);
       s.m_padded = padded;
@@ -262,9 +290,10 @@ int upload_set(cfmm_ctx* ctx, int type) {
       continue;
     }
     gam[(size_t)p] = s.gamma[(size_t)i];
-    last = make_int2((int)(s.Ai[2 * i] - 1), (int)(s.Ai[2 * i + 1] - 1));
+    last = make_int2(oa[(size_t)i], ob[(size_t)i]);
     ai[(size_t)p] = last;
-    gidx[(size_t)p] = s.gidx[(size_t)i];
+    // bit 62 of the global index marks a pool stored with its tokens exchanged
+    gidx[(size_t)p] = s.gidx[(size_t)i] | (s.swapped[(size_t)i] ? (1ll << 62) : 0);
   }
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
@@ -276,7 +305,8 @@ int upload_set(cfmm_ctx* ctx, int type) {
     for (int64_t p = 0; p < mp; ++p) {
       const int64_t i = s.order[(size_t)p];
       if (i < 0) continue;
-      r[(size_t)p] = make_double2(s.R[2 * i], s.R[2 * i + 1]);
+      r[(size_t)p] = s.swapped[(size_t)i] ? make_double2(s.R[2 * i + 1], s.R[2 * i])
+                                          : make_double2(s.R[2 * i], s.R[2 * i + 1]);
       ok = ok && fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
            fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
     }
@@ -835,7 +865,8 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   }
   std::vector<double2> newR((size_t)count);
   for (int64_t j = 0; j < count; ++j) {
-    newR[(size_t)j] = make_double2(R[2 * j], R[2 * j + 1]);
+    newR[(size_t)j] = s.swapped[(size_t)(first + j)] ? make_double2(R[2 * j + 1], R[2 * j])
+                                                     : make_double2(R[2 * j], R[2 * j + 1]);
     if (!fast_range_ok(R[2 * j]) || !fast_range_ok(R[2 * j + 1])) s.in_fast_range = false;
   }
   DevBuf<double2> d_new;
@@ -871,6 +902,10 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "orient_by_degree")) {
+    if (ctx->finalized)
+      return fail(ctx, CFMM_ERR_STATE, "orient_by_degree fixes the pool layout: set it before cfmm_finalize");
+    ctx->orient_by_degree = value != 0;
   } else if (!strcmp(key, "b_red_pools")) {
     if (value < 0 || value > 7) return fail(ctx, CFMM_ERR_INVALID, "b_red_pools out of range");
     ctx->b_red_pools = (int)value;

@@ -249,10 +249,13 @@ __global__ void scatter_trades_kernel(const double2* __restrict__ D,
                                       double2* __restrict__ outL, int64_t m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const int64_t o = orig[i];
+  int64_t o = orig[i];
   if (o < 0) return;  // padding pool
-  outD[o] = D[i];
-  outL[o] = L[i];
+  const bool swapped = (o >> 62) & 1;  // stored with its two tokens exchanged
+  o &= ~(1ll << 62);
+  const double2 d = D[i], l = L[i];
+  outD[o] = swapped ? make_double2(d.y, d.x) : d;
+  outL[o] = swapped ? make_double2(l.y, l.x) : l;
 }
 
 // R[pos[j]] = newR[j]

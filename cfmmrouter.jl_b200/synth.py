@@ -28,6 +28,23 @@ def product_pools(m: int, n_tokens: int, seed: int = 1234):
     return R, gamma, token_pairs(rng, m, n_tokens)
 
 
+def product_pools_skewed(m: int, n_tokens: int, alpha: float = 1.0, seed: int = 1234):
+    """Like product_pools, but token popularity follows a Zipf law (rank^-alpha):
+    a few hub tokens (the WETH / USDC of a real DEX graph) sit in a large share
+    of the pools, on either side.  The reference's own generators are uniform;
+    this one exists to exercise hub contention."""
+    rng = np.random.default_rng(seed)
+    R = np.maximum(1000.0 * rng.random((m, 2)), 1e-3)
+    gamma = rng.choice(np.array([0.997, 1.0]), size=m)
+    w = 1.0 / np.arange(1, n_tokens + 1) ** alpha
+    w /= w.sum()
+    a = rng.choice(n_tokens, size=m, p=w) + 1
+    b = rng.choice(n_tokens, size=m, p=w) + 1
+    clash = a == b
+    b[clash] = (a[clash] % n_tokens) + 1
+    return R, gamma, np.stack([a, b], axis=1).astype(np.int64)
+
+
 def geomean_pools(m: int, n_tokens: int, seed: int = 4321):
     """(R, gamma, Ai, w) with w1 ~ U(0.05, 0.95), w2 = 1 - w1 (test/cfmms.jl:101)."""
     rng = np.random.default_rng(seed)

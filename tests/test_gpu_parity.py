@@ -290,6 +290,31 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
     p.close()
 
 
+@pytest.mark.parametrize("orient", [1, 0])
+def test_skewed_token_graph(cr, oracle, synth, orient):
+    """Zipf-distributed tokens (hubs on either side of many pools): per-pool
+    trades stay bit-exact and in insertion order whether or not pools are stored
+    with their tokens exchanged; Ψ within tolerance; reserves update correctly."""
+    m, n = 200_000, 5_000
+    R, g, Ai = synth.product_pools_skewed(m, n, alpha=1.0, seed=77)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, product=(R, g, Ai), pre={"orient_by_degree": orient})
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    psi, acc = p.sweep(v)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    assert np.array_equal(D, Do) and np.array_equal(L, Lo)
+    R2 = R.copy()
+    R2[1000:90_000] *= 1.25
+    p.update_reserves(0, 1000, R2[1000:90_000])
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    D2, L2 = oracle.sweep_product(R2, g, Ai, v, threads=8)
+    assert np.array_equal(D, D2) and np.array_equal(L, L2)
+    p.close()
+
+
 def test_device_resident_api(cr, oracle, synth):
     """cfmm_sweep_device (caller's buffer) and cfmm_sweep_device_view (zero-copy,
     ping-pong accumulators cleared in-kernel) over many consecutive sweeps."""

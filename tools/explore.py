@@ -72,6 +72,20 @@ def main():
         res.append(row)
         p.close()
 
+    if len(sys.argv) > 1 and sys.argv[1] == "skew":
+        for alpha in (0.8, 1.0, 1.2):
+            for orient in (1, 0):
+                p = cr.DevicePools(50_000)
+                p.set_option("orient_by_degree", orient)
+                p.add_product(*synth.product_pools_skewed(10_000_000, 50_000, alpha=alpha))
+                p.finalize()
+                nu = synth.dual_prices(50_000, "near")
+                d_nu = torch.from_numpy(nu).to(dev)
+                d_psi = torch.zeros(50_001, dtype=torch.float64, device=dev)
+                us = time_sweeps(p, d_nu, d_psi, 10)
+                print(json.dumps({"tag": f"c5 zipf alpha={alpha} orient={orient}", "us": round(list(us.values())[0], 2)}), flush=True)
+                p.close()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "other":
         run("geomean 500k warm", 500_000, 10_000, "geomean", "near", iters=50)
         run("geomean 5M econ", 5_000_000, 10_000, "geomean", "near", iters=10)
