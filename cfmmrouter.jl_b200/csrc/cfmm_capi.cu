@@ -195,7 +195,7 @@ constexpr TmaVariant kTmaVariants[] = {
     {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
     {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
     {256, 3, 2, 3200, 2},  // 10: 98 KB, 2 CTAs/SM, 16 warps
-    {288, 3, 3, 1600, 2},  // 11: 106 KB, 2 CTAs/SM, 18 warps, 3 stages
+    {288, 3, 2, 3200, 2},  // 11: 104 KB, 2 CTAs/SM, 18 warps, <= 112 regs
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 

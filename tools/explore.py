@@ -98,9 +98,8 @@ def main():
     M, N = 10_000_000, 50_000
     for nu in ("near", "wide", "ones"):
         run("c5 tma", M, N, "product", nu)
-    for nr in (1, 2, 3):
-        run(f"c5 tma b_red_pools={nr}", M, N, "product", "near", b_red_pools=nr)
-    run("c5 tma b_red_pools=1 wide", M, N, "product", "wide", b_red_pools=1)
+
+
     return
     run("c5 tma warp-aggregated a-RED", M, N, "product", "near", a_red_per_thread=0)
     run("c5 tma reference-order math", M, N, "product", "near", gradient_math=0)
