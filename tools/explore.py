@@ -39,10 +39,13 @@ def main():
     res = []
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    PRE = ("tma_variant", "orient_by_degree")
+
     def run(tag, m, n, kind, nu_kind="near", iters=30, use_flush=False, **opts):
         p = cr.DevicePools(n)
-        if "tma_variant" in opts:
-            p.set_option("tma_variant", opts["tma_variant"])
+        for k in PRE:
+            if k in opts:
+                p.set_option(k, opts[k])
         if kind == "product":
             p.add_product(*synth.product_pools(m, n))
             bpp = 32
@@ -55,7 +58,7 @@ def main():
             bpp = 32 + 16 * 4
         p.finalize()
         for k, v in opts.items():
-            if k != "tma_variant":
+            if k not in PRE:
                 p.set_option(k, v)
         if kind == "univ3":
             rng = np.random.default_rng(3)
@@ -96,6 +99,12 @@ def main():
         run("univ3 5M", 5_000_000, 50_000, "univ3", iters=10)
         return
     M, N = 10_000_000, 50_000
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":
+        run("c5 tma", M, N, "product", "near")
+        run("c5 tma orient=0", M, N, "product", "near", orient_by_degree=0)
+        run("c5 tma", M, N, "product", "near")
+        run("c5 tma orient=0", M, N, "product", "near", orient_by_degree=0)
+        return
     for nu in ("near", "wide", "ones"):
         run("c5 tma", M, N, "product", nu)
 
