@@ -290,7 +290,7 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
     p.close()
 
 
-@pytest.mark.parametrize("orient", [1, 0])
+@pytest.mark.parametrize("orient", [-1, 1, 0])
 def test_skewed_token_graph(cr, oracle, synth, orient):
     """Zipf-distributed tokens (hubs on either side of many pools): per-pool
     trades stay bit-exact and in insertion order whether or not pools are stored
