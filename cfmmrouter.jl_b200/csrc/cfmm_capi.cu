@@ -453,12 +453,12 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
-template <int V, bool ECON, int NRED = 0>
+template <int V, bool ECON, int NRED = 0, bool SKEW = false>
 int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                            cudaStream_t st) {
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW>;
   static int occ = 0;
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -483,7 +483,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
       (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0,
-      ctx->exact | (ctx->a_red_per_thread ? 0 : 16) | (s.skewed ? 32 : 0), fx);
+      ctx->exact | (ctx->a_red_per_thread ? 0 : 16), fx);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   return CFMM_OK;
@@ -509,6 +509,9 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(10)
     CFMM_TMA_CASE(11)
     default:
+      if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
+        return econ ? launch_product_tma_cfg<0, true, 0, true>(ctx, s, d_v, d_psi, st)
+                    : launch_product_tma_cfg<0, false, 0, true>(ctx, s, d_v, d_psi, st);
       if (econ && ctx->b_red_pools == 1) return launch_product_tma_cfg<0, true, 1>(ctx, s, d_v, d_psi, st);
       if (econ && ctx->b_red_pools == 2) return launch_product_tma_cfg<0, true, 2>(ctx, s, d_v, d_psi, st);
       if (econ && ctx->b_red_pools == 3) return launch_product_tma_cfg<0, true, 3>(ctx, s, d_v, d_psi, st);
