@@ -45,6 +45,7 @@ SYMBOLS = {
     "cfmm_sweep_device_view": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cfmm_get_trades": (C.c_int, [_ctx, _dp, _dp]),
     "cfmm_update_reserves": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _dp]),
+    "cfmm_apply_trades": (C.c_int, [_ctx]),
     "cfmm_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "cfmm_last_sweep_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
     "cfmm_launch_count": (C.c_int64, [_ctx]),

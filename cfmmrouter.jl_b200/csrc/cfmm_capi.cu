@@ -903,6 +903,39 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   return CFMM_OK;
 }
 
+int cfmm_apply_trades(cfmm_ctx* ctx) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!ctx->has_trades)
+    return fail(ctx, CFMM_ERR_STATE,
+                "no materialising sweep has run (call cfmm_sweep with materialize=1)");
+  if (ctx->sets[CFMM_POOL_UNIV3].m > 0)
+    return fail(ctx, CFMM_ERR_INVALID,
+                "cfmm_apply_trades: UniV3 pools have no explicit reserves (R + γΔ − Λ is defined for "
+                "ProductTwoCoin / GeometricMeanTwoCoin only)");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf<int> flag;
+  std::vector<int> zero(1, 0);
+  for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) {
+    PoolSet& s = ctx->sets[t];
+    if (s.m == 0) continue;
+    if (s.d_outD.n != (size_t)s.m_padded)
+      return fail(ctx, CFMM_ERR_STATE, "trades of this pool type were never materialised");
+    CU_TRY(ctx, flag.upload(zero));
+    const int threads = 256;
+    cfmm::apply_trades_kernel<<<(unsigned)((s.m_padded + threads - 1) / threads), threads, 0, ctx->stream>>>(
+        s.d_R.p, s.d_gam.p, s.d_outD.p, s.d_outL.p, s.d_gidx.p, s.m_padded, flag.p);
+    ctx->launches++;
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    flag.release();
+    if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "apply_trades failed: %s", cudaGetErrorString(e));
+    if (h) s.in_fast_range = false;  // later sweeps take the generic (guarded) form
+  }
+  return CFMM_OK;
+}
+
 int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return CFMM_ERR_INVALID;
   if (!strcmp(key, "exact")) {

@@ -258,6 +258,25 @@ __global__ void scatter_trades_kernel(const double2* __restrict__ D,
   outL[o] = swapped ? make_double2(l.y, l.x) : l;
 }
 
+// R <- (R + γ·Δ) − Λ from the materialised trades of the same device order
+// (the update the reference's tests use, test/cfmms.jl:10: R⁺ = R + γ*Δ - Λ);
+// *out_of_range is raised when a new reserve leaves the guard-free range.
+__global__ void apply_trades_kernel(double2* __restrict__ R, const double* __restrict__ gam,
+                                    const double2* __restrict__ D, const double2* __restrict__ L,
+                                    const int64_t* __restrict__ gidx, int64_t m,
+                                    int* __restrict__ out_of_range) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  if (gidx[i] < 0) return;  // padding pool
+  const double g = gam[i];
+  const double2 r = R[i], d = D[i], l = L[i];
+  double2 n;
+  n.x = __dsub_rn(__dadd_rn(r.x, __dmul_rn(g, d.x)), l.x);
+  n.y = __dsub_rn(__dadd_rn(r.y, __dmul_rn(g, d.y)), l.y);
+  R[i] = n;
+  if (!in_fast_range(n.x) || !in_fast_range(n.y)) atomicOr(out_of_range, 1);
+}
+
 // R[pos[j]] = newR[j]
 __global__ void update_reserves_kernel(double2* __restrict__ R,
                                        const int64_t* __restrict__ pos,

@@ -151,6 +151,10 @@ class DevicePools:
         self._chk(self._lib.cfmm_get_trades(self._ctx, _dp(D), _dp(L)))
         return D, L
 
+    def apply_trades(self):
+        """R <- R + γΔ − Λ on the device, from the last materialising sweep."""
+        self._chk(self._lib.cfmm_apply_trades(self._ctx))
+
     def update_reserves(self, pool_type: int, first: int, R):
         R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 2)
         self._chk(self._lib.cfmm_update_reserves(self._ctx, int(pool_type), int(first), len(R), _dp(R)))
@@ -416,6 +420,9 @@ def update_reserves(r: Router):
     two-coin pools, on the host objects and on the device."""
     for D, L, c in zip(r.Δs, r.Λs, r.cfmms):
         if isinstance(c, (ProductTwoCoin, GeometricMeanTwoCoin)):
-            c.R = c.R + c.gamma * D - L
-    r.sync_reserves()
+            c.R = c.R + c.gamma * D - L  # same operation order as the device kernel: bit-identical
+    if any(isinstance(c, UniV3) for c in r.cfmms):
+        r.sync_reserves()  # mixed set: push the two-coin reserves from the host objects
+    else:
+        r._pools.apply_trades()  # on the device, from the materialised trades: no upload
     return None

@@ -138,6 +138,14 @@ int cfmm_get_trades(cfmm_ctx *ctx, double *Delta, double *Lambda);
 int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
                          const double *R);
 
+/* Apply the trades of the last materialising sweep to the device-resident
+ * reserves: R <- R + γΔ − Λ for every ProductTwoCoin / GeometricMeanTwoCoin pool
+ * (the update the reference intends with update_reserves!(r), src/router.jl:127-132,
+ * whose per-CFMM method is defined nowhere; formula from test/cfmms.jl:10).
+ * Lets a caller route repeatedly on evolving state without re-uploading pools.
+ * Fails with CFMM_ERR_INVALID if the context holds UniV3 pools. */
+int cfmm_apply_trades(cfmm_ctx *ctx);
+
 /* Tunables.  Keys: "exact" (1 = evaluate all four closed forms exactly as
  * written in the reference for every pool; 0 = default, bit-identical fast
  * path that evaluates only the non-zero side, falling back to the full form

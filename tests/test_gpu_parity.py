@@ -463,6 +463,44 @@ def test_update_reserves(cr, oracle, synth):
     p.close()
 
 
+def test_apply_trades_on_device(cr, oracle, synth):
+    """cfmm_apply_trades: R <- R + γΔ − Λ on the device, bit-identical to the same
+    numpy expression; the next sweep sees the new reserves (both kernels)."""
+    n = 6_000
+    R, g, Ai = synth.product_pools(80_000, n, seed=41)
+    Rg, gg, Ag, wg = synth.geomean_pools(20_000, n, seed=42)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, product=(R, g, Ai), geomean=(Rg, gg, Ag, wg))
+    with pytest.raises(cr.CFMMError):
+        p.apply_trades()  # nothing materialised yet
+    p.sweep(v, materialize=True)
+    D, L = p.trades()
+    p.apply_trades()
+    R2 = R + g[:, None] * D[:80_000] - L[:80_000]
+    Rg2 = Rg + gg[:, None] * D[80_000:] - L[80_000:]
+    v2 = synth.dual_prices(n, "near")
+    p.sweep(v2, materialize=True)
+    Dn, Ln = p.trades()
+    Do, Lo = oracle.sweep_product(R2, g, Ai, v2, threads=8)
+    assert np.array_equal(Dn[:80_000], Do) and np.array_equal(Ln[:80_000], Lo)
+    Dg, Lg = oracle.sweep_geomean(Rg2, gg, Ag, wg, v2, threads=8)
+    tol = 1e-12 * (np.max(Rg2, axis=1) / gg)[:, None]
+    assert np.all(np.abs(Dn[80_000:] - Dg) <= tol) and np.all(np.abs(Ln[80_000:] - Lg) <= tol)
+    psi, acc = p.sweep(v2)
+    check_psi(oracle, np.concatenate([Ai, Ag]), Dn, Ln, v2, n, psi, acc,
+              R=np.concatenate([R2, Rg2]), g=np.concatenate([g, gg]))
+    # after trading to the no-arbitrage point at v, the pools do not trade at v again
+    # (fee-less pools would be exactly at their no-trade boundary; with fees: inside the band)
+    p2 = make_pools(cr, n, product=(R[g < 1], g[g < 1], Ai[g < 1]))
+    p2.sweep(v, materialize=True)
+    p2.apply_trades()
+    p2.sweep(v, materialize=True)
+    D3, L3 = p2.trades()
+    assert np.all(D3 <= 1e-9 * R[g < 1]) and np.all(L3 <= 1e-9 * R[g < 1])
+    p.close()
+    p2.close()
+
+
 def test_nan_propagates_like_julia_max(cr, oracle):
     # Julia's max(x, 0) propagates NaN (CUDA fmax would not)
     R = np.array([[np.nan, 1.0], [1.0, 2.0]])
