@@ -18,7 +18,7 @@ using CFMMRouter
 using CFMMRouter: CFMM, ProductTwoCoin, GeometricMeanTwoCoin, UniV3, Objective,
                   f, grad!, lower_limit, upper_limit
 using LBFGSB
-import CFMMRouter: route!, find_arb!, netflows!, netflows
+import CFMMRouter: route!, find_arb!, netflows!, netflows, update_reserves!
 
 export B200Router, sync_reserves!
 
@@ -167,6 +167,22 @@ function netflows!(ψ, r::B200Router)
     return nothing
 end
 netflows(r::B200Router) = (ψ = zero(r.v); netflows!(ψ, r); ψ)
+
+# A working update_reserves!(r) (the reference's, src/router.jl:127-132, calls a per-CFMM
+# method that is defined nowhere): R <- R + γΔ − Λ (test/cfmms.jl:10) applied on the device
+# from the materialised trades, and mirrored on the host objects with the same expression.
+function update_reserves!(r::B200Router)
+    for (Δ, Λ, c) in zip(r.Δs, r.Λs, r.cfmms)
+        (c isa ProductTwoCoin || c isa GeometricMeanTwoCoin) || continue
+        c.R .= c.R .+ c.γ .* Δ .- Λ
+    end
+    if any(c -> c isa UniV3, r.cfmms)
+        sync_reserves!(r)                       # mixed set: push the two-coin reserves
+    else
+        chk(r.ctx, ccall((:cfmm_apply_trades, LIB), Cint, (Ptr{Cvoid},), r.ctx))
+    end
+    return nothing
+end
 
 # The reference reads cfmm.R live on every sweep; push mutated reserves explicitly.
 function sync_reserves!(r::B200Router)
