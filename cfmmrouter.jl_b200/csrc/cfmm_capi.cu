@@ -183,6 +183,7 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
 // product_sweep_tma instantiations: {THREADS, L, S, NBMAX, MINB}
 struct TmaVariant {
   int threads, L, S, nbmax, minb;
+  bool seq = false;  // sequential per-pool form (low registers, many warps)
 };
 constexpr TmaVariant kTmaVariants[] = {
     {320, 3, 2, 3200, 2},  // 0 (default): 110 KB smem, 2 CTAs/SM, 20 warps, 100 regs (no spill)
@@ -197,6 +198,10 @@ constexpr TmaVariant kTmaVariants[] = {
     {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
     {256, 3, 2, 3200, 2},  // 10: 98 KB, 2 CTAs/SM, 16 warps
     {288, 3, 2, 3200, 2},  // 11: 104 KB, 2 CTAs/SM, 18 warps, <= 112 regs
+    {1024, 3, 2, 1600, 1, true},  // 12: sequential, 1 CTA/SM, 32 warps, <= 64 regs
+    {768, 3, 2, 3200, 1, true},   // 13: sequential, 1 CTA/SM, 24 warps, <= 85 regs
+    {512, 3, 2, 800, 2, true},    // 14: sequential, 2 CTAs/SM, 32 warps, <= 64 regs
+    {384, 3, 2, 1600, 2, true},   // 15: sequential, 2 CTAs/SM, 24 warps, <= 85 regs
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 
@@ -458,7 +463,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
                            cudaStream_t st) {
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq>;
   static int occ = 0;
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -508,6 +513,10 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(9)
     CFMM_TMA_CASE(10)
     CFMM_TMA_CASE(11)
+    CFMM_TMA_CASE(12)
+    CFMM_TMA_CASE(13)
+    CFMM_TMA_CASE(14)
+    CFMM_TMA_CASE(15)
     default:
       if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
         return econ ? launch_product_tma_cfg<0, true, 0, true>(ctx, s, d_v, d_psi, st)

@@ -261,7 +261,7 @@ def test_inrange_math(cr):
     p.close()
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 7, 9, 10, 11])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15])
 @pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7)])
 def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
     """Every tile shape of the b-bucketed TMA kernel (several buckets at

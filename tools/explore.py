@@ -99,6 +99,11 @@ def main():
         run("univ3 5M", 5_000_000, 50_000, "univ3", iters=10)
         return
     M, N = 10_000_000, 50_000
+    if len(sys.argv) > 1 and sys.argv[1] == "seq":
+        run("c5 tma (default)", M, N, "product", "near")
+        for var in (12, 13, 14, 15):
+            run(f"c5 tma_variant={var} (sequential)", M, N, "product", "near", tma_variant=var)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
         run("c5 tma", M, N, "product", "near")
         run("c5 tma orient=0", M, N, "product", "near", orient_by_degree=0)
