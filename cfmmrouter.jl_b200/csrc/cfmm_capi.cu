@@ -186,7 +186,7 @@ struct TmaVariant {
   bool seq = false;  // sequential per-pool form (low registers, many warps)
 };
 constexpr TmaVariant kTmaVariants[] = {
-    {320, 3, 2, 3200, 2},  // 0 (default): 110 KB smem, 2 CTAs/SM, 20 warps, 100 regs (no spill)
+    {448, 3, 2, 1600, 2, true},  // 0 (default): sequential form, 109 KB smem, 2 CTAs/SM, 28 warps, 72 regs (no spill)
     {256, 5, 2, 2048, 2},  // 1: 112 KB, 2 CTAs/SM
     {256, 3, 3, 1600, 2},  // 2: 97 KB, 2 CTAs/SM, 3 stages
     {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
@@ -202,8 +202,16 @@ constexpr TmaVariant kTmaVariants[] = {
     {768, 3, 2, 3200, 1, true},   // 13: sequential, 1 CTA/SM, 24 warps, <= 85 regs
     {512, 3, 2, 800, 2, true},    // 14: sequential, 2 CTAs/SM, 32 warps, <= 64 regs
     {384, 3, 2, 1600, 2, true},   // 15: sequential, 2 CTAs/SM, 24 warps, <= 85 regs
+    {256, 3, 2, 1600, 3, true},   // 16: sequential, 3 CTAs/SM, 24 warps
+    {320, 3, 2, 3200, 2},         // 17: interleaved form, 2 CTAs/SM, 20 warps, 96 regs (the shape of the SKEW instantiation)
+    {384, 3, 2, 2400, 2, true},   // 18: sequential, 2 CTAs/SM, 24 warps, wider buckets
+    {256, 5, 2, 1600, 2, true},   // 19: sequential, 2 CTAs/SM, 16 warps, 5 pools/thread
+    {480, 3, 2, 1000, 2, true},   // 20: sequential, 2 CTAs/SM, 30 warps, <= 64 regs
+    {288, 3, 2, 1200, 3, true},   // 21: sequential, 3 CTAs/SM, 27 warps, <= 72 regs
+    {320, 3, 2, 800, 3, true},    // 22: sequential, 3 CTAs/SM, 30 warps, <= 64 regs
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
+constexpr int kSkewVariant = 17;  // layout used when finalize detects hub tokens (and the default shape was asked for)
 
 inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
 
@@ -262,7 +270,8 @@ int upload_set(cfmm_ctx* ctx, int type) {
   if (type == CFMM_POOL_PRODUCT && ctx->tma_variant >= 0) {
     // b-bucketed order for the TMA kernel: (bucket(b), a), each bucket padded
     // to whole tiles with zero-reserve pools (Δ = Λ = 0 at any ν).
-    const TmaVariant& tv = kTmaVariants[ctx->tma_variant];
+    const int variant = (s.skewed && ctx->tma_variant == 0) ? kSkewVariant : ctx->tma_variant;
+    const TmaVariant& tv = kTmaVariants[variant];
     const int64_t tile = (int64_t)tv.threads * tv.L;
     const int64_t n = ctx->n_tokens;
     const int64_t B = (n + tv.nbmax - 1) / tv.nbmax;
@@ -283,7 +292,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
       s.order.swap(order);
       s.m_padded = padded;
       s.tma_ok = true;
-      s.tma_variant = ctx->tma_variant;
+      s.tma_variant = variant;
       s.nb = (int)nb;
       tile_bucket.resize((size_t)(padded / tile));
       for (int64_t k = 0; k < B; ++k)
@@ -517,13 +526,21 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(13)
     CFMM_TMA_CASE(14)
     CFMM_TMA_CASE(15)
-    default:
+    CFMM_TMA_CASE(16)
+    CFMM_TMA_CASE(18)
+    CFMM_TMA_CASE(19)
+    CFMM_TMA_CASE(20)
+    CFMM_TMA_CASE(21)
+    CFMM_TMA_CASE(22)
+    case kSkewVariant:
       if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
-        return econ ? launch_product_tma_cfg<0, true, 0, true>(ctx, s, d_v, d_psi, st)
-                    : launch_product_tma_cfg<0, false, 0, true>(ctx, s, d_v, d_psi, st);
-      if (econ && ctx->b_red_pools == 1) return launch_product_tma_cfg<0, true, 1>(ctx, s, d_v, d_psi, st);
-      if (econ && ctx->b_red_pools == 2) return launch_product_tma_cfg<0, true, 2>(ctx, s, d_v, d_psi, st);
-      if (econ && ctx->b_red_pools == 3) return launch_product_tma_cfg<0, true, 3>(ctx, s, d_v, d_psi, st);
+        return econ ? launch_product_tma_cfg<kSkewVariant, true, 0, true>(ctx, s, d_v, d_psi, st)
+                    : launch_product_tma_cfg<kSkewVariant, false, 0, true>(ctx, s, d_v, d_psi, st);
+      if (econ && ctx->b_red_pools == 1) return launch_product_tma_cfg<kSkewVariant, true, 1>(ctx, s, d_v, d_psi, st);
+      if (econ && ctx->b_red_pools == 2) return launch_product_tma_cfg<kSkewVariant, true, 2>(ctx, s, d_v, d_psi, st);
+      return econ ? launch_product_tma_cfg<kSkewVariant, true>(ctx, s, d_v, d_psi, st)
+                  : launch_product_tma_cfg<kSkewVariant, false>(ctx, s, d_v, d_psi, st);
+    default:
       return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
                   : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);
   }

@@ -101,7 +101,7 @@ def main():
     M, N = 10_000_000, 50_000
     if len(sys.argv) > 1 and sys.argv[1] == "seq":
         run("c5 tma (default)", M, N, "product", "near")
-        for var in (12, 13, 14, 15):
+        for var in (17, 20, 21, 22):
             run(f"c5 tma_variant={var} (sequential)", M, N, "product", "near", tma_variant=var)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
