@@ -38,7 +38,6 @@ sys.path.insert(0, ROOT)
 
 METRIC = "find_arb_pools_per_sec_per_dual_gradient_sweep"
 UNIT = "pools/s"
-BYTES_PER_POOL = {"product": 32, "geomean": 48}  # R1,R2,γ fp64 + 2 x int32 (+ w1,w2)
 
 WORKLOADS = {
     # name: (pools per GPU, n_tokens, kind)

@@ -91,7 +91,7 @@ struct cfmm_ctx {
   PoolSet sets[3];
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DevBuf<double> d_nu, d_psi;  // n, n+1
+  DevBuf<double> d_nu;  // n
   double* h_stage = nullptr;   // pinned, n+1
   int sm_count = 148;
   // options
@@ -681,7 +681,6 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   CREATE_TRY(cudaEventCreate(&ctx->ev0));
   CREATE_TRY(cudaEventCreate(&ctx->ev1));
   CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
-  CREATE_TRY(ctx->d_psi.alloc((size_t)n_tokens + 1));
   CREATE_TRY(ctx->d_grid_done.alloc(1));
   CREATE_TRY(cudaMemset(ctx->d_grid_done.p, 0, sizeof(unsigned long long)));
   memset(&ctx->fx_pending, 0, sizeof(ctx->fx_pending));
@@ -704,7 +703,6 @@ void cfmm_destroy(cfmm_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
-  ctx->d_psi.release();
   ctx->d_grid_done.release();
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();

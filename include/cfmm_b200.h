@@ -146,17 +146,28 @@ int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
  * Fails with CFMM_ERR_INVALID if the context holds UniV3 pools. */
 int cfmm_apply_trades(cfmm_ctx *ctx);
 
-/* Tunables.  Keys: "exact" (1 = evaluate all four closed forms exactly as
- * written in the reference for every pool; 0 = default, bit-identical fast
- * path that evaluates only the non-zero side, falling back to the full form
- * near ties), "blocks_per_sm" (0 = occupancy-derived), "profile" (see
- * cfmm_profile_read), "tma_variant" (tile shape of the ProductTwoCoin TMA
- * kernel, fixed at cfmm_finalize; -1 = first-generation kernel only),
- * "use_tma" (0 = first-generation kernel on the same layout),
- * "gradient_math" (gradient-only ProductTwoCoin sweeps, where per-pool trades
- * are not observable: 1 = default, economized closed form, <= ~3 ulp of the
- * reserve per pool; 0 = the reference's operation order, bit-identical per
- * pool.  Materialising sweeps and "exact" are always bit-identical). */
+/* Tunables (none is needed for normal use).
+ *   "exact"            1 = evaluate all four closed forms exactly as written in the
+ *                      reference for every pool; 0 (default) = evaluate only the side that
+ *                      can trade, falling back to the full form near ties (same bits).
+ *   "gradient_math"    gradient-only sweeps, where per-pool trades are not observable:
+ *                      1 (default) = economized closed forms (ProductTwoCoin: one rsqrt +
+ *                      one rcp; GeometricMean: one pow), <= ~3 ulp of the reserve per pool;
+ *                      0 = the reference's operation order, bit-identical per pool.
+ *                      Materialising sweeps and "exact" are always bit-identical.
+ *   "tma_variant"      tile shape / form of the ProductTwoCoin TMA kernel; fixes the pool
+ *                      layout, so it must be set before cfmm_finalize (-1 = none).
+ *   "orient_by_degree" store each ProductTwoCoin pool with its higher-degree token first:
+ *                      -1 (default) = only when finalize detects hub tokens, 0 never,
+ *                      1 always; before cfmm_finalize.
+ *   "use_tma"          0 = run the first-generation kernel on the same layout.
+ *   "a_red_per_thread" / "b_red_pools" / "blocks_per_sm"   scatter-path experiments.
+ *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
+ *                      in the sweep kernel's tail; 0 = separate exchange launch.
+ *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol
+ *                      (default: two-shot for more than two ranks); after cfmm_comm_attach.
+ *   "sweep_events"     0 = do not record the two CUDA events cfmm_last_sweep_ms needs.
+ *   "profile"          N = time the next N kernel launches (cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
 /* Device time (ms, CUDA events on the sweep stream) of the kernels of the

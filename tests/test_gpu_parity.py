@@ -501,6 +501,71 @@ def test_apply_trades_on_device(cr, oracle, synth):
     p2.close()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_operation_sequences(cr, oracle, synth, seed):
+    """State-machine fuzz: random sequences of gradient-only / materialising
+    sweeps at changing ν, reserve pushes, on-device trade application and option
+    toggles; after every step Ψ, acc (and trades, when materialised) are checked
+    against the oracle run on a host mirror of the pool state."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(40, 9000))
+    mp_, mg_ = int(rng.integers(1, 60_000)), int(rng.integers(0, 8_000))
+    R, g, Ai = synth.product_pools(mp_, n, seed=100 + seed)
+    Rg, gg, Ag, wg = synth.geomean_pools(max(mg_, 1), n, seed=200 + seed)
+    if mg_ == 0:
+        Rg, gg, Ag, wg = Rg[:0], gg[:0], Ag[:0], wg[:0]
+    p = cr.DevicePools(n)
+    p.set_option("tma_variant", int(rng.choice([0, 0, 17, 10, -1])))
+    p.add_product(R, g, Ai)
+    if mg_:
+        p.add_geomean(Rg, gg, Ag, wg)
+    p.finalize()
+    R, Rg = R.copy(), Rg.copy()
+    A = np.concatenate([Ai, Ag])
+    last_mat = None
+
+    def reference(v):
+        D1, L1 = oracle.sweep_product(R, g, Ai, v, threads=8)
+        if mg_:
+            D2, L2 = oracle.sweep_geomean(Rg, gg, Ag, wg, v, threads=8)
+            return np.concatenate([D1, D2]), np.concatenate([L1, L2])
+        return D1, L1
+
+    for step in range(14):
+        op = rng.choice(["grad", "grad", "mat", "push", "apply", "toggle"])
+        v = synth.dual_prices(n, str(rng.choice(["near", "wide", "ones"])), seed=int(rng.integers(1 << 30)))
+        if op == "grad":
+            psi, acc = p.sweep(v)
+            Do, Lo = reference(v)
+            check_psi(oracle, A, Do, Lo, v, n, psi, acc, R=np.concatenate([R, Rg]) * 64, g=np.concatenate([g, gg]))
+        elif op == "mat":
+            psi, acc = p.sweep(v, materialize=True)
+            D, L = p.trades()
+            Do, Lo = reference(v)
+            assert np.array_equal(D[:mp_], Do[:mp_]) and np.array_equal(L[:mp_], Lo[:mp_])
+            if mg_:
+                tol = 1e-12 * (np.max(Rg, axis=1) / gg)[:, None]
+                assert np.all(np.abs(D[mp_:] - Do[mp_:]) <= tol) and np.all(np.abs(L[mp_:] - Lo[mp_:]) <= tol)
+            check_psi(oracle, A, D, L, v, n, psi, acc)
+            last_mat = (D, L)
+        elif op == "push":
+            lo = int(rng.integers(0, mp_))
+            hi = int(rng.integers(lo, mp_)) + 1
+            R[lo:hi] *= rng.uniform(0.5, 1.5, size=(hi - lo, 1))
+            p.update_reserves(0, lo, R[lo:hi])
+            last_mat = None
+        elif op == "apply" and last_mat is not None:
+            D, L = last_mat
+            p.apply_trades()
+            R = R + g[:, None] * D[:mp_] - L[:mp_]
+            if mg_:
+                Rg = Rg + gg[:, None] * D[mp_:] - L[mp_:]
+            last_mat = None
+        elif op == "toggle":
+            p.set_option(str(rng.choice(["gradient_math", "use_tma", "a_red_per_thread"])), int(rng.integers(0, 2)))
+    p.close()
+
+
 def test_nan_propagates_like_julia_max(cr, oracle):
     # Julia's max(x, 0) propagates NaN (CUDA fmax would not)
     R = np.array([[np.nan, 1.0], [1.0, 2.0]])
