@@ -17,6 +17,7 @@
 
 #include "../../include/cfmm_b200.h"
 #include "peer_exchange.cuh"
+#include "pool_layout.hpp"
 #include "sweep_kernels.cuh"
 #include "product_tma.cuh"
 
@@ -215,91 +216,45 @@ constexpr int kSkewVariant = 17;  // layout used when finalize detects hub token
 
 inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
 
-// stable counting sort of pools by first token (0-based keys oa[i])
-void token_sort(const std::vector<int>& oa, int64_t n_tokens, std::vector<int64_t>& order) {
-  const int64_t m = (int64_t)oa.size();
-  std::vector<int64_t> head((size_t)n_tokens + 1, 0);
-  for (int64_t i = 0; i < m; ++i) head[(size_t)oa[(size_t)i] + 1]++;
-  for (int64_t t = 0; t < n_tokens; ++t) head[(size_t)t + 1] += head[(size_t)t];
-  order.assign((size_t)m, 0);
-  for (int64_t i = 0; i < m; ++i) order[(size_t)head[(size_t)oa[(size_t)i]]++] = i;
+inline cfmm::TileShape tile_shape_of(int variant) {
+  cfmm::TileShape t;
+  if (variant >= 0) {
+    t.tile = (int64_t)kTmaVariants[variant].threads * kTmaVariants[variant].L;
+    t.nbmax = kTmaVariants[variant].nbmax;
+  }
+  return t;
+}
+
+// layout of one pool type (pool_layout.hpp): ProductTwoCoin gets the bucketed TMA
+// layout of the requested tile shape (the interleaved shape when hubs are
+// detected and the default was asked for); the other types are a-sorted only.
+cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m,
+                            int* variant_used) {
+  const bool product = type == CFMM_POOL_PRODUCT;
+  const int v = product ? ctx->tma_variant : -1;
+  const cfmm::TileShape normal = tile_shape_of(v);
+  const cfmm::TileShape skew = (product && v == 0) ? tile_shape_of(kSkewVariant) : normal;
+  cfmm::PoolLayout lay = cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree,
+                                                 product, normal, skew);
+  *variant_used = (lay.used_skew_shape && v == 0) ? kSkewVariant : v;
+  return lay;
 }
 
 int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
   if (s.m == 0) return CFMM_OK;
   const int64_t m = s.m;
-  // Device orientation of each pool: (oa, ob) 0-based.  ProductTwoCoin is exactly
-  // symmetric under exchanging its two tokens (k = R1·R2 commutes; every closed
-  // form of one side is the other side's with the roles swapped), so each pool
-  // is stored with its HIGHER-DEGREE token first: hub tokens of a skewed market
-  // graph then sit on the run side (register accumulation, warp-uniform ν
-  // loads) instead of hammering one shared-memory slot with fp64 CAS adds.
-  std::vector<int> oa((size_t)m), ob((size_t)m);
-  s.swapped.assign((size_t)m, 0);
-  s.skewed = false;
-  {
-    std::vector<int64_t> deg;
-    if (type == CFMM_POOL_PRODUCT && ctx->orient_by_degree != 0) {
-      deg.assign((size_t)ctx->n_tokens, 0);
-      for (int64_t i = 0; i < m; ++i) {
-        deg[(size_t)s.Ai[2 * i] - 1]++;
-        deg[(size_t)s.Ai[2 * i + 1] - 1]++;
-      }
-      // hub detection: some token sits in far more pools than the average token.
-      // On uniform graphs orientation only perturbs the layout (measured -2.6 %),
-      // so in auto mode (-1) it is applied to skewed graphs only.
-      int64_t max_deg = 0;
-      for (int64_t d : deg) max_deg = d > max_deg ? d : max_deg;
-      const double mean_deg = 2.0 * (double)m / (double)ctx->n_tokens;
-      s.skewed = (double)max_deg > 4.0 * mean_deg + 64.0;
-      if (ctx->orient_by_degree < 0 && !s.skewed) deg.clear();
-    }
-    for (int64_t i = 0; i < m; ++i) {
-      const int a = (int)(s.Ai[2 * i] - 1), b = (int)(s.Ai[2 * i + 1] - 1);
-      const bool sw = !deg.empty() && deg[(size_t)b] > deg[(size_t)a];
-      s.swapped[(size_t)i] = sw;
-      oa[(size_t)i] = sw ? b : a;
-      ob[(size_t)i] = sw ? a : b;
-    }
-  }
-  token_sort(oa, ctx->n_tokens, s.order);
-  s.m_padded = m;
-  s.tma_ok = false;
-  std::vector<int> tile_bucket;
-  if (type == CFMM_POOL_PRODUCT && ctx->tma_variant >= 0) {
-    // b-bucketed order for the TMA kernel: (bucket(b), a), each bucket padded
-    // to whole tiles with zero-reserve pools (Δ = Λ = 0 at any ν).
-    const int variant = (s.skewed && ctx->tma_variant == 0) ? kSkewVariant : ctx->tma_variant;
-    const TmaVariant& tv = kTmaVariants[variant];
-    const int64_t tile = (int64_t)tv.threads * tv.L;
-    const int64_t n = ctx->n_tokens;
-    const int64_t B = (n + tv.nbmax - 1) / tv.nbmax;
-    const int64_t nb = (n + B - 1) / B;
-    std::vector<int64_t> cnt((size_t)B + 1, 0);
-    for (int64_t i = 0; i < m; ++i) cnt[(size_t)(ob[(size_t)i] / nb) + 1]++;
-    int64_t padded = 0;
-    for (int64_t k = 0; k < B; ++k) padded += (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
-    if (padded <= 2 * m + 8 * tile) {  // otherwise too sparse per bucket: first-generation kernel
-      std::vector<int64_t> start((size_t)B + 1, 0);  // padded start of each bucket
-      for (int64_t k = 0; k < B; ++k)
-        start[(size_t)k + 1] = start[(size_t)k] + (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
-      std::vector<int64_t> order((size_t)padded, -1), fill(start.begin(), start.end() - 1);
-      for (int64_t p = 0; p < m; ++p) {  // stable: keeps the a-order inside a bucket
-        const int64_t i = s.order[(size_t)p];
-        order[(size_t)fill[(size_t)(ob[(size_t)i] / nb)]++] = i;
-      }
-      s.order.swap(order);
-      s.m_padded = padded;
-      s.tma_ok = true;
-      s.tma_variant = variant;
-      s.nb = (int)nb;
-      tile_bucket.resize((size_t)(padded / tile));
-      for (int64_t k = 0; k < B; ++k)
-        for (int64_t t = start[(size_t)k] / tile; t < start[(size_t)k + 1] / tile; ++t)
-          tile_bucket[(size_t)t] = (int)k;
-    }
-  }
+  int variant = -1;
+  cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m, &variant);
+  const std::vector<int>&oa = lay.oa, &ob = lay.ob;
+  s.swapped = lay.swapped;
+  s.skewed = lay.skewed;
+  s.order = lay.order;
+  s.m_padded = lay.m_padded;
+  s.tma_ok = lay.bucketed;
+  s.tma_variant = variant;
+  s.nb = (int)lay.nb;
+  const std::vector<int>& tile_bucket = lay.tile_bucket;
   const int64_t mp = s.m_padded;
   std::vector<double> gam((size_t)mp, 1.0);
   std::vector<int2> ai((size_t)mp);
@@ -1039,6 +994,40 @@ void* cfmm_host_alloc(size_t bytes) {
 }
 void cfmm_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+// Test hook (no CUDA call): the device layout finalize would build for m
+// ProductTwoCoin pools.  info[6] = {m_padded, nb, bucketed, skewed, tile, variant};
+// order_out [cap] (device position -> pool index, -1 = padding), tile_bucket_out
+// [cap / tile], swapped_out [m] are filled when cap >= m_padded (call with cap = 0 first).
+int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t* Ai, int orient,
+                              int variant, int64_t cap, int64_t* order_out,
+                              int32_t* tile_bucket_out, uint8_t* swapped_out, int64_t* info) {
+  if (!Ai || !info || m < 0 || n_tokens < 2 || variant < -1 || variant >= kNumTmaVariants)
+    return CFMM_ERR_INVALID;
+  for (int64_t i = 0; i < 2 * m; ++i)
+    if (Ai[i] < 1 || Ai[i] > n_tokens) return CFMM_ERR_INVALID;
+  cfmm_ctx fake;
+  fake.n_tokens = n_tokens;
+  fake.tma_variant = variant;
+  fake.orient_by_degree = orient;
+  int used = -1;
+  const cfmm::PoolLayout lay = layout_for(&fake, CFMM_POOL_PRODUCT, Ai, m, &used);
+  const int64_t tile = used >= 0 ? (int64_t)kTmaVariants[used].threads * kTmaVariants[used].L : 0;
+  info[0] = lay.m_padded;
+  info[1] = lay.nb;
+  info[2] = lay.bucketed;
+  info[3] = lay.skewed;
+  info[4] = tile;
+  info[5] = used;
+  if (cap >= lay.m_padded && order_out) {
+    for (int64_t p = 0; p < lay.m_padded; ++p) order_out[p] = lay.order[(size_t)p];
+    if (tile_bucket_out)
+      for (size_t t = 0; t < lay.tile_bucket.size(); ++t) tile_bucket_out[t] = lay.tile_bucket[t];
+    if (swapped_out)
+      for (int64_t i = 0; i < m; ++i) swapped_out[i] = lay.swapped[(size_t)i];
+  }
+  return CFMM_OK;
 }
 
 // Test hook: number of (a/b, sqrt a, sqrt b) results, over n host-provided

@@ -191,6 +191,15 @@ int cfmm_profile_reset(cfmm_ctx *ctx);
 int cfmm_selftest_inrange_math(cfmm_ctx *ctx, const double *a, const double *b,
                                int64_t n, int64_t *mismatches);
 
+/* Test hook, needs no device: the layout cfmm_finalize would give m ProductTwoCoin
+ * pools (Ai 1-based [2m]) for tile shape `variant` and orientation mode `orient`.
+ * info[6] = {m_padded, bucket width, bucketed?, hubs detected?, tile size, variant used};
+ * with cap >= m_padded also order_out [m_padded] (device position -> pool index, -1 =
+ * padding), tile_bucket_out [m_padded / tile] and swapped_out [m]. */
+int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t *Ai, int orient,
+                              int variant, int64_t cap, int64_t *order_out,
+                              int32_t *tile_bucket_out, uint8_t *swapped_out, int64_t *info);
+
 /* ---- pinned host memory helpers ------------------------------------------- */
 void *cfmm_host_alloc(size_t bytes);
 void cfmm_host_free(void *p);
