@@ -247,3 +247,50 @@ def test_sweep_and_fold_match_per_pool(oracle):
     assert accf == acc and np.array_equal(Gf, G)
     accs, Gs = oracle.soa_sweep_product(R, g, Ai, v, n, threads=3)
     assert np.isclose(accs, acc, rtol=1e-12) and np.allclose(Gs, G, rtol=1e-12, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------
+# property tests (hypothesis): the reference's predicate on arbitrary pools
+# ---------------------------------------------------------------------------
+
+try:
+    from hypothesis import given, settings, strategies as st
+
+    pos = st.floats(min_value=1e-3, max_value=1e6, allow_nan=False, allow_infinity=False)
+    fee = st.floats(min_value=0.5, max_value=1.0)
+
+    @settings(max_examples=300, deadline=None)
+    @given(R1=pos, R2=pos, gamma=fee, v1=pos, v2=pos)
+    def test_product_optimality_hypothesis(R1, R2, gamma, v1, v2):
+        import oracle_lib
+        o = oracle_lib.load()
+        R, nu = np.array([R1, R2]), np.array([v1, v2])
+        D, L = o.product_arb(R, gamma, nu)
+        # feasibility + at most one side trades + KKT (test/cfmms.jl:3-22; the ≈ / sqrt(eps)
+        # slacks of that predicate are absolute, so scale ϕ to O(1) first)
+        assert np.all(D >= 0) and np.all(L >= 0)
+        assert not (D[0] > 0 and D[1] > 0) and not (L[0] > 0 and L[1] > 0)
+        Rp = R + gamma * D - L
+        assert abs(Rp[0] * Rp[1] - R1 * R2) <= 1e-9 * R1 * R2
+        g = np.array([Rp[1], Rp[0]])
+        assert max(gamma * g[i] / nu[i] for i in range(2)) <= min(g[i] / nu[i] for i in range(2)) * (1 + 1e-9)
+
+    @settings(max_examples=200, deadline=None)
+    @given(R1=pos, R2=pos, gamma=fee, v1=pos, v2=pos, w1=st.floats(min_value=0.05, max_value=0.95))
+    def test_geomean_optimality_hypothesis(R1, R2, gamma, v1, v2, w1):
+        import oracle_lib
+        o = oracle_lib.load()
+        R, nu, w = np.array([R1, R2]), np.array([v1, v2]), np.array([w1, 1 - w1])
+        D, L = o.geomean_arb(R, w, gamma, nu)
+        assert np.all(D >= 0) and np.all(L >= 0)
+        Rp = R + gamma * D - L
+        # (when a trade nearly drains a reserve, R − Λ cancels and the closed form's own
+        # rounding is amplified: the tolerances are relative to what is left of the reserve)
+        amp = float(np.max(R / np.maximum(Rp, 1e-300)))
+        phi0, phi1 = phi_geomean(R, w), phi_geomean(Rp, w)
+        assert abs(phi1 - phi0) <= 1e-12 * amp * phi0 + 1e-9 * phi0
+        g = grad_phi_geomean(Rp, w)
+        assert max(gamma * g[i] / nu[i] for i in range(2)) <= \
+            min(g[i] / nu[i] for i in range(2)) * (1 + 1e-12 * amp + 1e-9)
+except ImportError:  # hypothesis is optional
+    pass
