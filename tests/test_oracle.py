@@ -259,7 +259,7 @@ try:
     pos = st.floats(min_value=1e-3, max_value=1e6, allow_nan=False, allow_infinity=False)
     fee = st.floats(min_value=0.5, max_value=1.0)
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=300, deadline=None, derandomize=True)
     @given(R1=pos, R2=pos, gamma=fee, v1=pos, v2=pos)
     def test_product_optimality_hypothesis(R1, R2, gamma, v1, v2):
         import oracle_lib
@@ -275,7 +275,7 @@ try:
         g = np.array([Rp[1], Rp[0]])
         assert max(gamma * g[i] / nu[i] for i in range(2)) <= min(g[i] / nu[i] for i in range(2)) * (1 + 1e-9)
 
-    @settings(max_examples=200, deadline=None)
+    @settings(max_examples=200, deadline=None, derandomize=True)
     @given(R1=pos, R2=pos, gamma=fee, v1=pos, v2=pos, w1=st.floats(min_value=0.05, max_value=0.95))
     def test_geomean_optimality_hypothesis(R1, R2, gamma, v1, v2, w1):
         import oracle_lib
