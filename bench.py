@@ -135,6 +135,20 @@ class ClockSampler:
                 pass
             time.sleep(0.005)
 
+    def _sample_once(self):
+        n = self._nvml
+        try:
+            self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+            try:
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for bit, name in self._BITS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def start(self):
         if self._nvml:
             self._thr = threading.Thread(target=self._loop, daemon=True)
@@ -142,6 +156,7 @@ class ClockSampler:
 
     def stop(self):
         if self._thr:
+            self._sample_once()  # at least one sample taken while the last steps are in flight
             self._stop.set()
             self._thr.join()
 
@@ -305,6 +320,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler_ref = [None]
+
     def timed_region(steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -312,6 +329,8 @@ def run_ours(args):
         for _ in range(steps):
             step()
         e1.record(stream)
+        if sampler_ref[0] is not None:
+            sampler_ref[0]._sample_once()  # GPU still busy with the queued steps
         barrier()
         return e0.elapsed_time(e1)
 
@@ -322,9 +341,11 @@ def run_ours(args):
         # ---- timed region 1: K steps, nothing but the sweeps on the stream -> `value`
         l0 = pools.launch_count
         sampler = ClockSampler(local_rank)
+        sampler_ref[0] = sampler if sampler._nvml else None
         sampler.start()
         ms_total = timed_region(args.steps)
         sampler.stop()
+        sampler_ref[0] = None
         launches = pools.launch_count - l0
         # ---- timed region 2: the same K steps with a CUDA-event pair around every
         # kernel launch (on the launching stream) -> per-kernel durations for `roofline`
