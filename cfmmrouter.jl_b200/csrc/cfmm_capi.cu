@@ -100,6 +100,7 @@ struct cfmm_ctx {
   int debug_skip = 0;  // measurement only (tools/explore.py)
   int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
+  int skew_interleaved = 0;  // hub-detected graphs: 1 = use the interleaved 320-thread shape instead of the default sequential one (before finalize)
   int orient_by_degree = -1; // ProductTwoCoin: store each pool with its higher-degree token first: -1 auto (skewed graphs only), 0 never, 1 always (fixed at finalize)
   int b_red_pools = 0;       // how many of a thread's L pools send Ψ[b] by global RED instead of the shared slice
   int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
@@ -233,10 +234,10 @@ cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, in
   const bool product = type == CFMM_POOL_PRODUCT;
   const int v = product ? ctx->tma_variant : -1;
   const cfmm::TileShape normal = tile_shape_of(v);
-  const cfmm::TileShape skew = (product && v == 0) ? tile_shape_of(kSkewVariant) : normal;
+  const cfmm::TileShape skew = (product && v == 0 && ctx->skew_interleaved) ? tile_shape_of(kSkewVariant) : normal;
   cfmm::PoolLayout lay = cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree,
                                                  product, normal, skew);
-  *variant_used = (lay.used_skew_shape && v == 0) ? kSkewVariant : v;
+  *variant_used = (lay.used_skew_shape && v == 0 && ctx->skew_interleaved) ? kSkewVariant : v;
   return lay;
 }
 
@@ -496,6 +497,9 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
       return econ ? launch_product_tma_cfg<kSkewVariant, true>(ctx, s, d_v, d_psi, st)
                   : launch_product_tma_cfg<kSkewVariant, false>(ctx, s, d_v, d_psi, st);
     default:
+      if (s.skewed)  // hub tokens: the SKEW instantiation of the default (sequential) shape
+        return econ ? launch_product_tma_cfg<0, true, 0, true>(ctx, s, d_v, d_psi, st)
+                    : launch_product_tma_cfg<0, false, 0, true>(ctx, s, d_v, d_psi, st);
       return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
                   : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);
   }
@@ -927,6 +931,10 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
+  } else if (!strcmp(key, "skew_interleaved")) {
+    if (ctx->finalized)
+      return fail(ctx, CFMM_ERR_STATE, "skew_interleaved fixes the pool layout: set it before cfmm_finalize");
+    ctx->skew_interleaved = value != 0;
   } else if (!strcmp(key, "orient_by_degree")) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "orient_by_degree fixes the pool layout: set it before cfmm_finalize");

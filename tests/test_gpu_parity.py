@@ -301,7 +301,7 @@ def test_skewed_token_graph(cr, oracle, synth, orient):
     m, n = 200_000, 5_000
     R, g, Ai = synth.product_pools_skewed(m, n, alpha=1.0, seed=77)
     v = synth.dual_prices(n, "wide")
-    p = make_pools(cr, n, product=(R, g, Ai), pre={"orient_by_degree": orient})
+    p = make_pools(cr, n, product=(R, g, Ai), pre={"orient_by_degree": orient, "skew_interleaved": int(orient == 1)})
     Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
     psi, acc = p.sweep(v)
     check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)

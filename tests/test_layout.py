@@ -92,7 +92,7 @@ def test_skewed_graph_orientation(cr, orient):
     if orient == 0:
         assert not lay["swapped"].any() and lay["variant"] == 0
     else:
-        assert lay["skewed"] and lay["variant"] == 17  # the interleaved shape carries the SKEW kernel
+        assert lay["skewed"] and lay["variant"] == 0  # default shape, SKEW instantiation
         assert np.array_equal(lay["swapped"].astype(bool), deg[b] > deg[a])  # higher-degree token first
         hub = int(np.argmax(deg))
         first = np.where(lay["swapped"].astype(bool), b, a)

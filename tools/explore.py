@@ -76,10 +76,10 @@ def main():
         p.close()
 
     if len(sys.argv) > 1 and sys.argv[1] == "skew":
-        for alpha in (0.8, 1.0, 1.2):
-            for orient in (1, 0):
+        for alpha in (1.0, 1.2):
+            for orient in (1, 2):  # 1 = default sequential SKEW shape, 2 = interleaved SKEW shape
                 p = cr.DevicePools(50_000)
-                p.set_option("orient_by_degree", orient)
+                p.set_option("skew_interleaved", 1 if orient == 2 else 0)
                 p.add_product(*synth.product_pools_skewed(10_000_000, 50_000, alpha=alpha))
                 p.finalize()
                 nu = synth.dual_prices(50_000, "near")
