@@ -11,6 +11,21 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    _ensure_built()
+
+
+def _ensure_built():
+    """A fresh checkout has no build artefacts (they are git-ignored): build the
+    product library (nvcc cross-compiles for sm_100a without a GPU) and the oracle
+    once, exactly as __graft_entry__.build() does."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "cfmmrouter.jl_b200", "libcfmm_b200.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "cfmmrouter.jl_b200", "csrc")], check=True,
+                       capture_output=True)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")
