@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/cfmm_b200.h"
@@ -114,6 +115,11 @@ struct cfmm_ctx {
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived
+  // resident CTAs per SM of every kernel instantiation this context has launched.
+  // Per context, not per process: cudaFuncSetAttribute (the > 48 KB dynamic shared
+  // memory opt-in) acts on the current device only, and contexts of one process
+  // may sit on different devices and be driven from different host threads.
+  std::unordered_map<const void*, int> occupancy;
   int64_t launches = 0;
   std::string err;
   cfmm::PeerExchange comm;
@@ -390,8 +396,8 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   const int64_t m_all = s.m_padded;  // includes the zero-trade padding pools, if any
   int64_t blocks = (m_all + per_block - 1) / per_block;
   // persistent-style grid: one wave of resident CTAs (148 SMs x occupancy)
-  static int occ_mat = 0, occ_grad = 0;
-  int& occ = mat ? occ_mat : occ_grad;
+  int& occ = ctx->occupancy[mat ? reinterpret_cast<const void*>(&cfmm::sweep_kernel<P, true, U>)
+                                 : reinterpret_cast<const void*>(&cfmm::sweep_kernel<P, false, U>)];
   if (occ == 0) {
     if (mat)
       CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -429,7 +435,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
   auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq>;
-  static int occ = 0;
+  int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::kSmemBytes));

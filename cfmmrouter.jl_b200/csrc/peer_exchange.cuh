@@ -217,6 +217,10 @@ class PeerExchange {
       err_ = "cfmm_comm_export must be called before cfmm_comm_attach";
       return false;
     }
+    if (attached_) {  // epochs restart at 0 on attach; the receive areas must be fresh
+      err_ = "already attached (cfmm_comm_detach, then export and attach again)";
+      return false;
+    }
     world_ = world;
     rank_ = rank;
     // every element is an independent push+poll: enough CTAs to cover the vector once

@@ -82,6 +82,11 @@ def test_two_contexts_one_process_peer_exchange(cr, oracle):
     from cfmmrouter_b200 import _lib
     world = 2
     pools = [_shard(cr, r, world) for r in range(world)]
+    # Strictly one device after the other, before any exchange: per-kernel state
+    # (the > 48 KB shared-memory opt-in, occupancy) is per device, so the second
+    # context must set it up again rather than inherit a process-wide cache.
+    local = [p.sweep(v) for p, v in pools]
+    assert all(np.all(np.isfinite(psi)) and np.isfinite(acc) for psi, acc in local)
     handles = b""
     for p, _ in pools:
         buf = (C.c_ubyte * _lib.COMM_HANDLE_BYTES)()

@@ -451,6 +451,59 @@ def test_error_codes(cr):
     p.close()
 
 
+def test_two_contexts_interleaved_on_one_device(cr, oracle, synth):
+    """Contexts are independent: per-context kernel set-up (shared-memory opt-in,
+    occupancy), ping-pong accumulators and streams.  Two pool sets swept
+    alternately must give what each gives alone, bit for bit when repeated."""
+    na, nb = 3_001, 977
+    A = synth.product_pools(150_007, na, seed=31)
+    B = synth.product_pools(90_001, nb, seed=32)
+    va, vb = synth.dual_prices(na, "wide", seed=1), synth.dual_prices(nb, "near", seed=2)
+    pa = make_pools(cr, na, product=A)
+    ra0 = pa.sweep(va)                       # context a fully warmed before b exists
+    pb = make_pools(cr, nb, product=B)
+    seen_a, seen_b = [], []
+    for _ in range(3):
+        seen_b.append(pb.sweep(vb))
+        seen_a.append(pa.sweep(va))
+    for (R, g, Ai), v, n, seen in ((A, va, na, seen_a), (B, vb, nb, seen_b)):
+        D, L = oracle.sweep_product(R, g, Ai, v)
+        for psi, acc in seen:
+            check_psi(oracle, Ai, D, L, v, n, psi, acc, R=R, g=g)
+    # materialising sweeps are per-pool bit-exact and do not disturb the other context
+    pa.sweep(va, materialize=True)
+    pb.sweep(vb, materialize=True)
+    for p, (R, g, Ai), v in ((pa, A, va), (pb, B, vb)):
+        D, L = oracle.sweep_product(R, g, Ai, v)
+        Dg, Lg = p.trades()
+        assert np.array_equal(Dg, D) and np.array_equal(Lg, L)
+    assert np.all(np.isfinite(ra0[0]))
+    pa.close()
+    pb.close()
+
+
+def test_comm_attach_twice_is_refused(cr):
+    """Exchange epochs restart at attach, so a second attach over used receive
+    areas is an error (detach + export + attach is the way to re-join)."""
+    import ctypes as C
+    from cfmmrouter_b200 import _lib
+    p = cr.DevicePools(4)
+    p.add_product([[10.0, 20.0]], [0.997], [[1, 3]])
+    p.finalize()
+    buf = (C.c_ubyte * _lib.COMM_HANDLE_BYTES)()
+    p._chk(p._lib.cfmm_comm_export(p._ctx, buf))
+    p._chk(p._lib.cfmm_comm_attach(p._ctx, 1, 0, bytes(buf)))      # world of one: no exchange
+    psi, acc = p.sweep(np.array([1.0, 1.0, 3.0, 1.0]))
+    assert np.isfinite(acc) and psi[1] == 0.0 and psi[3] == 0.0
+    with pytest.raises(cr.CFMMError) as e:
+        p._chk(p._lib.cfmm_comm_attach(p._ctx, 1, 0, bytes(buf)))
+    assert e.value.code == -5 and "already attached" in e.value.message
+    p._chk(p._lib.cfmm_comm_detach(p._ctx))
+    p._chk(p._lib.cfmm_comm_export(p._ctx, buf))
+    p._chk(p._lib.cfmm_comm_attach(p._ctx, 1, 0, bytes(buf)))
+    p.close()
+
+
 def test_update_reserves(cr, oracle, synth):
     n = 20
     R, g, Ai = synth.product_pools(1000, n, seed=11)
