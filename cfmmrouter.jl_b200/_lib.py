@@ -50,6 +50,7 @@ SYMBOLS = {
     "cfmm_last_sweep_ms": (C.c_int, [_ctx, C.POINTER(C.c_float)]),
     "cfmm_launch_count": (C.c_int64, [_ctx]),
     "cfmm_profile_read": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "cfmm_profile_read_times": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64)]),
     "cfmm_profile_reset": (C.c_int, [_ctx]),
     "cfmm_selftest_inrange_math": (C.c_int, [_ctx, _dp, _dp, C.c_int64, _ip]),
     "cfmm_debug_product_layout": (C.c_int, [C.c_int64, C.c_int64, _ip, C.c_int, C.c_int, C.c_int64, _ip,

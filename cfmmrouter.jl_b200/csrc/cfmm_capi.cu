@@ -995,6 +995,22 @@ int cfmm_profile_read(cfmm_ctx* ctx, int type, double* total_ms, int64_t* launch
   return CFMM_OK;
 }
 
+int cfmm_profile_read_times(cfmm_ctx* ctx, int type, float* ms_out, int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out || cap < 0 || (cap > 0 && !ms_out)) return CFMM_ERR_INVALID;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  int64_t cnt = 0;
+  for (size_t i = 0; i < ctx->prof.used; ++i) {
+    if (ctx->prof.type[i] != type) continue;
+    if (cnt < cap) {
+      CU_TRY(ctx, cudaEventSynchronize(ctx->prof.ev[2 * i + 1]));
+      CU_TRY(ctx, cudaEventElapsedTime(&ms_out[cnt], ctx->prof.ev[2 * i], ctx->prof.ev[2 * i + 1]));
+    }
+    ++cnt;
+  }
+  *n_out = cnt;
+  return CFMM_OK;
+}
+
 int cfmm_profile_reset(cfmm_ctx* ctx) {
   if (!ctx) return CFMM_ERR_INVALID;
   ctx->prof.used = 0;

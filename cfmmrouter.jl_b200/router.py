@@ -141,6 +141,17 @@ class DevicePools:
         self._chk(self._lib.cfmm_profile_read(self._ctx, int(pool_type), C.byref(ms), C.byref(cnt)))
         return float(ms.value), int(cnt.value)
 
+    def profile_times(self, pool_type: int):
+        """Per-launch durations (ms, launch order) of the event-timed kernels of one pool type."""
+        cnt = C.c_int64(0)
+        self._chk(self._lib.cfmm_profile_read_times(self._ctx, int(pool_type), None, 0, C.byref(cnt)))
+        out = np.zeros(int(cnt.value), dtype=np.float32)
+        if len(out):
+            self._chk(self._lib.cfmm_profile_read_times(self._ctx, int(pool_type),
+                                                        out.ctypes.data_as(C.POINTER(C.c_float)),
+                                                        len(out), C.byref(cnt)))
+        return out
+
     def profile_reset(self):
         self._chk(self._lib.cfmm_profile_reset(self._ctx))
 

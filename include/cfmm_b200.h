@@ -183,6 +183,9 @@ int64_t cfmm_launch_count(const cfmm_ctx *ctx);
  * multi-GPU exchange kernel); it synchronises on the recorded events.
  * cfmm_profile_reset re-arms the same N pairs. */
 int cfmm_profile_read(cfmm_ctx *ctx, int type, double *total_ms, int64_t *launches);
+/* The individual durations (ms) behind cfmm_profile_read, in launch order: fills
+ * ms_out[0 .. min(cap, *n_out)) and sets *n_out to the number recorded for `type`. */
+int cfmm_profile_read_times(cfmm_ctx *ctx, int type, float *ms_out, int64_t cap, int64_t *n_out);
 int cfmm_profile_reset(cfmm_ctx *ctx);
 
 /* Test hook: counts, over n operand pairs (host arrays), the results of the

@@ -482,6 +482,26 @@ def test_two_contexts_interleaved_on_one_device(cr, oracle, synth):
     pb.close()
 
 
+def test_profile_per_launch_times(cr, synth):
+    """cfmm_profile_read_times: the individual event-bracketed durations add up to
+    cfmm_profile_read's total, one per armed launch of that pool type."""
+    n = 500
+    p = make_pools(cr, n, product=synth.product_pools(40_000, n, seed=5),
+                   geomean=synth.geomean_pools(10_000, n, seed=6))
+    v = synth.dual_prices(n, "near")
+    p.set_option("profile", 8)          # 4 sweeps x (product kernel + geomean kernel)
+    for _ in range(5):                   # the 5th sweep is past the armed window
+        p.sweep(v)
+    for t in (0, 1):
+        total, cnt = p.profile_read(t)
+        times = p.profile_times(t)
+        assert cnt == 4 and times.shape == (4,) and np.all(times > 0)
+        assert abs(float(times.astype(np.float64).sum()) - total) <= 1e-6 * total
+    assert p.profile_times(2).shape == (0,)
+    p.set_option("profile", 0)
+    p.close()
+
+
 def test_comm_attach_twice_is_refused(cr):
     """Exchange epochs restart at attach, so a second attach over used receive
     areas is an error (detach + export + attach is the way to re-join)."""
