@@ -191,7 +191,8 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
 // product_sweep_tma instantiations: {THREADS, L, S, NBMAX, MINB}
 struct TmaVariant {
   int threads, L, S, nbmax, minb;
-  bool seq = false;  // sequential per-pool form (low registers, many warps)
+  bool seq = false;   // sequential per-pool form (low registers, many warps)
+  bool bulk = false;  // Ψ[b] slice flushed by one TMA bulk reduction (needs an even bucket width)
 };
 constexpr TmaVariant kTmaVariants[] = {
     {448, 3, 2, 1600, 2, true},  // 0 (default): sequential form, 109 KB smem, 2 CTAs/SM, 28 warps, 72 regs (no spill)
@@ -217,6 +218,10 @@ constexpr TmaVariant kTmaVariants[] = {
     {480, 3, 2, 1000, 2, true},   // 20: sequential, 2 CTAs/SM, 30 warps, <= 64 regs
     {288, 3, 2, 1200, 3, true},   // 21: sequential, 3 CTAs/SM, 27 warps, <= 72 regs
     {320, 3, 2, 800, 3, true},    // 22: sequential, 3 CTAs/SM, 30 warps, <= 64 regs
+    // 23: variant 0 with the Ψ[b] slice flushed by cp.reduce.async.bulk (UBLKRED.ADD.F64).
+    // Written after the round's GPU budget was spent: compiles, NOT yet run on hardware,
+    // reachable only through the "tma_variant" option and in no test's parameter list.
+    {448, 3, 2, 1600, 2, true, true},
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kSkewVariant = 17;  // layout used when finalize detects hub tokens (and the default shape was asked for)
@@ -228,6 +233,7 @@ inline cfmm::TileShape tile_shape_of(int variant) {
   if (variant >= 0) {
     t.tile = (int64_t)kTmaVariants[variant].threads * kTmaVariants[variant].L;
     t.nbmax = kTmaVariants[variant].nbmax;
+    t.nb_align = kTmaVariants[variant].bulk ? 2 : 1;
   }
   return t;
 }
@@ -434,7 +440,7 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
                            cudaStream_t st) {
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq, tv.bulk>;
   int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -494,6 +500,7 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(20)
     CFMM_TMA_CASE(21)
     CFMM_TMA_CASE(22)
+    CFMM_TMA_CASE(23)
     case kSkewVariant:
       if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
         return econ ? launch_product_tma_cfg<kSkewVariant, true, 0, true>(ctx, s, d_v, d_psi, st)

@@ -16,6 +16,7 @@ namespace cfmm {
 struct TileShape {
   int64_t tile = 0;   // pools per tile (threads * L); 0 = no bucketing
   int64_t nbmax = 0;  // capacity of the shared ν / Ψ slices, in tokens
+  int64_t nb_align = 1;  // bucket width is a multiple of this (2: 16-byte bucket bases for bulk reductions)
 };
 
 struct PoolLayout {
@@ -77,7 +78,11 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
   // b-bucketed order: (bucket(b), a), each bucket padded to whole tiles
   const int64_t tile = shape.tile;
   const int64_t B = (n_tokens + shape.nbmax - 1) / shape.nbmax;
-  const int64_t nb = (n_tokens + B - 1) / B;
+  int64_t nb = (n_tokens + B - 1) / B;
+  if (shape.nb_align > 1) {  // round up; stays within the slice capacity when nbmax is a multiple too
+    const int64_t up = (nb + shape.nb_align - 1) / shape.nb_align * shape.nb_align;
+    if (up <= shape.nbmax) nb = up;
+  }
   std::vector<int64_t> cnt((size_t)B + 1, 0);
   for (int64_t i = 0; i < m; ++i) cnt[(size_t)(lay.ob[(size_t)i] / nb) + 1]++;
   int64_t padded = 0;

@@ -72,6 +72,22 @@ def test_uniform_graph_layout(cr, m, n, variant):
         assert lay["bucketed"]
 
 
+@pytest.mark.parametrize("m,n", [(40_000, 3001), (60_000, 20_011), (100_000, 50_000), (30_000, 1599)])
+def test_bulk_flush_variant_has_even_buckets(cr, m, n):
+    """Variant 23 flushes a bucket's Ψ[b] slice with one 16-byte-granular bulk
+    reduction: its bucket width (hence every bucket base) must be even, still
+    within the 1600-token slice; the default variant's layout is not touched."""
+    from cfmmrouter_b200 import synth
+    _, _, Ai = synth.product_pools(m, n, seed=m + n)
+    lay = layout(cr, n, Ai, variant=23)
+    check_invariants(Ai, n, lay)
+    assert lay["bucketed"] and lay["nb"] % 2 == 0 and lay["nb"] <= 1600
+    ref = layout(cr, n, Ai, variant=0)
+    B = -(-n // 1600)
+    assert ref["nb"] == -(-n // B)          # unchanged rule for the validated variant
+    assert lay["nb"] in (ref["nb"], ref["nb"] + 1)
+
+
 def test_sparse_buckets_fall_back_to_a_sorted(cr):
     from cfmmrouter_b200 import synth
     _, _, Ai = synth.product_pools(3000, 200_000, seed=1)  # 63+ buckets, ~50 pools each
