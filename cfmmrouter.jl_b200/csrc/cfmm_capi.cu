@@ -106,6 +106,7 @@ struct cfmm_ctx {
   int b_red_pools = 0;       // how many of a thread's L pools send Ψ[b] by global RED instead of the shared slice
   int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
   int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
+  int geomean_log2 = 0;   // staged experiment: gradient-only GeometricMean sweeps through exp2/log2 instead of pow
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
   unsigned long long epoch = 0;  // sweeps enqueued so far
   DevBuf<double> d_accum[2];     // ping-pong [Ψ; acc] accumulators, zeroed one sweep ahead in-kernel
@@ -562,7 +563,13 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     constexpr int PT = CFMM_POOL_GEOMEAN;
     if (s.m > 0) {
       cfmm::GeomeanPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_w.p};
-      if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      if (ctx->geomean_log2 && !mat) {
+        cfmm::GeomeanPoolsLog2 q;
+        static_cast<cfmm::GeomeanPools&>(q) = p;
+        if ((rc = launch_sweep(ctx, PT, q, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
+      } else if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) {
+        return rc;
+      }
     }
   }
   {
@@ -965,6 +972,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->a_red_per_thread = value != 0;
   } else if (!strcmp(key, "gradient_math")) {
     ctx->gradient_math = value != 0;
+  } else if (!strcmp(key, "geomean_log2")) {
+    ctx->geomean_log2 = value != 0;
   } else if (!strcmp(key, "use_tma")) {
     ctx->use_tma = value != 0;
   } else if (!strcmp(key, "debug_skip")) {

@@ -127,6 +127,17 @@ struct GeomeanPools {
   }
 };
 
+// Same pools; gradient-only sweeps take the power through exp2/log2 (see
+// geomean_arb_econ<true>).  A separate policy type = separate kernel instantiations,
+// so the validated GeomeanPools kernels are untouched.
+struct GeomeanPoolsLog2 : GeomeanPools {
+  __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
+                                       bool exact, bool econ) const {
+    if (econ && !exact) return geomean_arb_econ<true>(p.R.x, p.R.y, p.w.x, p.w.y, p.g, v1, v2);
+    return geomean_arb(p.R.x, p.R.y, p.w.x, p.w.y, p.g, v1, v2, exact);
+  }
+};
+
 struct Univ3Pools {
   const double* cp;       // current_price
   const double* gam;

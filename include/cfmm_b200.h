@@ -167,6 +167,8 @@ int cfmm_apply_trades(cfmm_ctx *ctx);
  *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol
  *                      (default: two-shot for more than two ranks); after cfmm_comm_attach.
  *   "sweep_events"     0 = do not record the two CUDA events cfmm_last_sweep_ms needs.
+ *   "geomean_log2"     staged experiment (not validated on hardware yet): 1 = gradient-only
+ *                      GeometricMean sweeps take the power as exp2(e*log2 t) instead of pow.
  *   "profile"          N = time the next N kernel launches (cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
