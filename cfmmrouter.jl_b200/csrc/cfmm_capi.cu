@@ -30,6 +30,10 @@ template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;  // owns its allocation: freed on every exit path
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) return cudaSuccess;
