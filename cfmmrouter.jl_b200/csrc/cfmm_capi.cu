@@ -198,6 +198,7 @@ struct TmaVariant {
   int threads, L, S, nbmax, minb;
   bool seq = false;   // sequential per-pool form (low registers, many warps)
   bool bulk = false;  // Ψ[b] slice flushed by one TMA bulk reduction (needs an even bucket width)
+  bool warpred = false;  // sequential form: the threads' last Ψ[a] runs merged across the warp before the RED
 };
 constexpr TmaVariant kTmaVariants[] = {
     {448, 3, 2, 1600, 2, true},  // 0 (default): sequential form, 109 KB smem, 2 CTAs/SM, 28 warps, 72 regs (no spill)
@@ -227,6 +228,8 @@ constexpr TmaVariant kTmaVariants[] = {
     // Written after the round's GPU budget was spent: compiles, NOT yet run on hardware,
     // reachable only through the "tma_variant" option and in no test's parameter list.
     {448, 3, 2, 1600, 2, true, true},
+    {448, 3, 2, 1600, 2, true, false, true},  // 24: variant 0 + warp-merged Ψ[a] runs (staged like 23)
+    {448, 3, 2, 1600, 2, true, true, true},   // 25: 23 + 24
 };
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kSkewVariant = 17;  // layout used when finalize detects hub tokens (and the default shape was asked for)
@@ -445,7 +448,8 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
                            cudaStream_t st) {
   constexpr TmaVariant tv = kTmaVariants[V];
   using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq, tv.bulk>;
+  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq, tv.bulk,
+                                      tv.warpred>;
   int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -506,6 +510,8 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
     CFMM_TMA_CASE(21)
     CFMM_TMA_CASE(22)
     CFMM_TMA_CASE(23)
+    CFMM_TMA_CASE(24)
+    CFMM_TMA_CASE(25)
     case kSkewVariant:
       if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
         return econ ? launch_product_tma_cfg<kSkewVariant, true, 0, true>(ctx, s, d_v, d_psi, st)

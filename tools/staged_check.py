@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """First GPU call of the next round (not product code): the two experiments staged
 after this round's GPU budget was spent -- `tma_variant` 23 (bulk-reduction slice
-flush) and option `geomean_log2` -- are checked against the validated default path
+flush), 24 (warp-merged Ψ[a] runs), 25 (both) and option `geomean_log2` -- are checked against the validated default path
 on the same inputs, then timed beside it.  Prints one JSON object per check; any
 "ok": false means the experiment stays off.
 
@@ -19,6 +19,7 @@ import cfmmrouter_b200 as cr
 from cfmmrouter_b200 import synth
 
 EPS = np.finfo(np.float64).eps
+STAGED = (23, 24, 25)
 
 
 def bracketed_us(pools, d_nu, iters=200):
@@ -43,7 +44,7 @@ def product_case(m, n, nu_kind, seed):
     R, g, Ai = synth.product_pools(m, n, seed=seed)
     v = synth.dual_prices(n, nu_kind)
     res, us = {}, {}
-    for variant in (0, 23):
+    for variant in (0,) + STAGED:
         p = cr.DevicePools(n)
         p.set_option("tma_variant", variant)
         p.add_product(R, g, Ai)
@@ -61,16 +62,18 @@ def product_case(m, n, nu_kind, seed):
     np.add.at(absG, Ai[:, 0] - 1, w)
     np.add.at(absG, Ai[:, 1] - 1, w)
     tol = 64 * EPS * absG + 1e-300
-    ok = True
-    worst = 0.0
-    for k in range(3):
-        d = np.abs(res[23][0][k][0] - res[0][0][k][0])
-        worst = max(worst, float(np.max(d / tol)))
-        ok &= bool(np.all(d <= tol)) and abs(res[23][0][k][1] - res[0][0][k][1]) <= float(np.sum(tol * v))
-    d = np.abs(res[23][1][0] - res[0][1][0])
-    ok &= bool(np.all(d <= tol))
-    return {"check": "tma_variant_23_vs_0", "m": m, "n": n, "nu": nu_kind, "ok": ok,
-            "worst_err_over_tol": worst, "median_us": {"variant0": us[0], "variant23": us[23]}}
+    out = []
+    for var in STAGED:
+        ok, worst = True, 0.0
+        for k in range(3):
+            d = np.abs(res[var][0][k][0] - res[0][0][k][0])
+            worst = max(worst, float(np.max(d / tol)))
+            ok &= bool(np.all(d <= tol)) and abs(res[var][0][k][1] - res[0][0][k][1]) <= float(np.sum(tol * v))
+        d = np.abs(res[var][1][0] - res[0][1][0])
+        ok &= bool(np.all(d <= tol))
+        out.append({"check": f"tma_variant_{var}_vs_0", "m": m, "n": n, "nu": nu_kind, "ok": ok,
+                    "worst_err_over_tol": worst, "median_us": {"variant0": us[0], f"variant{var}": us[var]}})
+    return out
 
 
 def geomean_case(m, n, seed):
@@ -101,9 +104,9 @@ def main():
     out = []
     for m, n, kind, seed in ((5_000, 7, "wide", 1), (200_003, 3_001, "near", 2), (300_000, 20_011, "wide", 3),
                              (1_000_000, 49_999, "near", 4), (10_000_000, 50_000, "near", 1234)):
-        r = product_case(m, n, kind, seed)
-        print(json.dumps(r), flush=True)
-        out.append(r)
+        for r in product_case(m, n, kind, seed):
+            print(json.dumps(r), flush=True)
+            out.append(r)
     for m, n, seed in ((50_000, 500, 5), (5_000_000, 10_000, 4321)):
         r = geomean_case(m, n, seed)
         print(json.dumps(r), flush=True)
