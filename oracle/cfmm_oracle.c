@@ -520,9 +520,13 @@ double oracle_soa_sweep_product(int64_t m, const double *R, const double *gamma,
   return acc;
 }
 
+/* Host cores the timing flavours may use.  omp_get_num_procs(), not
+ * omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1,
+ * which must not turn the CPU baseline into a single-thread run (every
+ * parallel region here passes an explicit num_threads clause). */
 int oracle_max_threads(void) {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return omp_get_num_procs();
 #else
   return 1;
 #endif
