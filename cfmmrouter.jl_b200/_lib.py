@@ -55,6 +55,8 @@ SYMBOLS = {
     "cfmm_selftest_inrange_math": (C.c_int, [_ctx, _dp, _dp, C.c_int64, _ip]),
     "cfmm_debug_product_layout": (C.c_int, [C.c_int64, C.c_int64, _ip, C.c_int, C.c_int, C.c_int64, _ip,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_uint8), _ip]),
+    "cfmm_debug_tile_schedule": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, C.c_int, C.c_int, C.c_int64,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), _ip]),
     "cfmm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cfmm_host_free": (None, [C.c_void_p]),
     "cfmm_comm_export": (C.c_int, [_ctx, C.c_void_p]),

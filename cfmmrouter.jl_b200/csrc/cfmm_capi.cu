@@ -71,18 +71,29 @@ struct PoolSet {
   DevBuf<int2> d_Ai, d_tick;
   DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
   int64_t total_ticks = 0;
-  int64_t m_padded = 0;        // product: arrays padded to whole TMA tiles, per b-bucket
+  int64_t m_padded = 0;        // product: arrays padded to whole 96-pool chunks, per b-bucket
   bool in_fast_range = false;  // every R, γ in [2^-100, 2^100] and γ <= 1
   bool tma_ok = false;         // b-bucketed layout built (product only)
-  int tma_variant = 0;         // tile shape the layout was built for
   int nb = 0;                  // bucket width in tokens
-  DevBuf<int> d_tile_bucket;   // bucket of every tile
+  std::vector<int> chunk_bucket;  // product: bucket of every chunk of the padded device order
+  DevBuf<int4> d_tile_desc;    // product: tile schedule of the TMA kernel (pool_layout.hpp) ...
+  DevBuf<int> d_cta_tile_start;  // ... and each CTA's tile range
+  int sched_grid = 0;          // grid the uploaded schedule was built for (0 = none yet)
+  int sched_max_chunks = 0;
+  // fixed-point Ψ[b] slice (product_tma.cuh): derived copy of the reserves with the
+  // second component scaled by 2^s_b, and the per-token 2^-s_b table
+  DevBuf<double2> d_Rs;
+  DevBuf<double> d_inv_scale, d_tok_sum;
+  DevBuf<double> d_ig;         // 1/γ per pool (device order), streamed by the economized gradient sweep
+  bool fixed_ok = false;       // the scaled copy is valid and every token fits the fixed-point rules
   std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
-    d_Ai.release(); d_tick.release(); d_gidx.release(); d_tile_bucket.release();
+    d_Ai.release(); d_tick.release(); d_gidx.release();
+    d_tile_desc.release(); d_cta_tile_start.release();
+    d_Rs.release(); d_inv_scale.release(); d_tok_sum.release(); d_ig.release();
   }
 };
 
@@ -103,14 +114,13 @@ struct cfmm_ctx {
   // options
   int exact = 0;
   int debug_skip = 0;  // measurement only (tools/explore.py)
-  int tma_variant = 0; // tile shape of the b-bucketed ProductTwoCoin layout (-1: none); fixed at finalize
+  int tma_variant = 0; // 0: b-bucketed ProductTwoCoin layout + TMA kernel; -1: a-sorted layout, first-generation kernel only (fixed at finalize)
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
-  int skew_interleaved = 0;  // hub-detected graphs: 1 = use the interleaved 320-thread shape instead of the default sequential one (before finalize)
   int orient_by_degree = -1; // ProductTwoCoin: store each pool with its higher-degree token first: -1 auto (skewed graphs only), 0 never, 1 always (fixed at finalize)
-  int b_red_pools = 0;       // how many of a thread's L pools send Ψ[b] by global RED instead of the shared slice
+  int psi_fixed_point = 1;   // Ψ[b] partials of the TMA kernel: 1 = 64-bit fixed point on native shared atomics when the pool set allows it, 0 = fp64 CAS adds
+  int tile_chunks = cfmm::kTmaWarps;  // chunks per tile of the schedule (<= 14; measurement knob)
   int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
-  int a_red_per_thread = 1;  // Ψ[a]: 1 = one RED per thread run (default), 0 = warp-aggregated RED per key
-  int geomean_log2 = 0;   // staged experiment: gradient-only GeometricMean sweeps through exp2/log2 instead of pow
+  int geomean_log2 = 1;   // gradient-only GeometricMean sweeps: power through exp2/log2 (1, default) or pow (0)
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
   unsigned long long epoch = 0;  // sweeps enqueued so far
   DevBuf<double> d_accum[2];     // ping-pong [Ψ; acc] accumulators, zeroed one sweep ahead in-kernel
@@ -193,89 +203,36 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
   ctx->n_pools += m;
 }
 
-// product_sweep_tma instantiations: {THREADS, L, S, NBMAX, MINB}
-struct TmaVariant {
-  int threads, L, S, nbmax, minb;
-  bool seq = false;   // sequential per-pool form (low registers, many warps)
-  bool bulk = false;  // Ψ[b] slice flushed by one TMA bulk reduction (needs an even bucket width)
-  bool warpred = false;  // sequential form: the threads' last Ψ[a] runs merged across the warp before the RED
-};
-constexpr TmaVariant kTmaVariants[] = {
-    {448, 3, 2, 1600, 2, true},  // 0 (default): sequential form, 109 KB smem, 2 CTAs/SM, 28 warps, 72 regs (no spill)
-    {256, 5, 2, 2048, 2},  // 1: 112 KB, 2 CTAs/SM
-    {256, 3, 3, 1600, 2},  // 2: 97 KB, 2 CTAs/SM, 3 stages
-    {512, 3, 2, 3200, 1},  // 3: 146 KB, 1 CTA/SM
-    {256, 3, 2, 1600, 3},  // 4: 73 KB, 3 CTAs/SM, 24 warps
-    {512, 3, 3, 3200, 1},  // 5: 195 KB, 1 CTA/SM, 3 stages
-    {768, 3, 2, 3200, 1},  // 6: 195 KB, 1 CTA/SM, 24 warps
-    {768, 2, 2, 3200, 1},  // 7: 147 KB, 1 CTA/SM, 24 warps, 2 pools/thread
-    {640, 3, 2, 3200, 1},  // 8: 171 KB, 1 CTA/SM, 20 warps
-    {384, 3, 2, 1600, 2},  // 9: 97 KB, 2 CTAs/SM, 24 warps (<= 85 regs)
-    {256, 3, 2, 3200, 2},  // 10: 98 KB, 2 CTAs/SM, 16 warps
-    {288, 3, 2, 3200, 2},  // 11: 104 KB, 2 CTAs/SM, 18 warps, <= 112 regs
-    {1024, 3, 2, 1600, 1, true},  // 12: sequential, 1 CTA/SM, 32 warps, <= 64 regs
-    {768, 3, 2, 3200, 1, true},   // 13: sequential, 1 CTA/SM, 24 warps, <= 85 regs
-    {512, 3, 2, 800, 2, true},    // 14: sequential, 2 CTAs/SM, 32 warps, <= 64 regs
-    {384, 3, 2, 1600, 2, true},   // 15: sequential, 2 CTAs/SM, 24 warps, <= 85 regs
-    {256, 3, 2, 1600, 3, true},   // 16: sequential, 3 CTAs/SM, 24 warps
-    {320, 3, 2, 3200, 2},         // 17: interleaved form, 2 CTAs/SM, 20 warps, 96 regs (the shape of the SKEW instantiation)
-    {384, 3, 2, 2400, 2, true},   // 18: sequential, 2 CTAs/SM, 24 warps, wider buckets
-    {256, 5, 2, 1600, 2, true},   // 19: sequential, 2 CTAs/SM, 16 warps, 5 pools/thread
-    {480, 3, 2, 1000, 2, true},   // 20: sequential, 2 CTAs/SM, 30 warps, <= 64 regs
-    {288, 3, 2, 1200, 3, true},   // 21: sequential, 3 CTAs/SM, 27 warps, <= 72 regs
-    {320, 3, 2, 800, 3, true},    // 22: sequential, 3 CTAs/SM, 30 warps, <= 64 regs
-    // 23: variant 0 with the Ψ[b] slice flushed by cp.reduce.async.bulk (UBLKRED.ADD.F64).
-    // Written after the round's GPU budget was spent: compiles, NOT yet run on hardware,
-    // reachable only through the "tma_variant" option and in no test's parameter list.
-    {448, 3, 2, 1600, 2, true, true},
-    {448, 3, 2, 1600, 2, true, false, true},  // 24: variant 0 + warp-merged Ψ[a] runs (staged like 23)
-    {448, 3, 2, 1600, 2, true, true, true},   // 25: 23 + 24
-};
-constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
-constexpr int kSkewVariant = 17;  // layout used when finalize detects hub tokens (and the default shape was asked for)
-
 inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kFastHi; }
 
-inline cfmm::TileShape tile_shape_of(int variant) {
-  cfmm::TileShape t;
-  if (variant >= 0) {
-    t.tile = (int64_t)kTmaVariants[variant].threads * kTmaVariants[variant].L;
-    t.nbmax = kTmaVariants[variant].nbmax;
-    t.nb_align = kTmaVariants[variant].bulk ? 2 : 1;
+// layout of one pool type (pool_layout.hpp): ProductTwoCoin gets the b-bucketed,
+// chunk-padded layout of the TMA kernel; the other types are a-sorted only.
+cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m) {
+  const bool product = type == CFMM_POOL_PRODUCT;
+  cfmm::TileShape shape;
+  if (product && ctx->tma_variant >= 0) {
+    shape.tile = cfmm::kTmaChunk;
+    shape.nbmax = cfmm::kTmaNbMax;
   }
-  return t;
+  return cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree, product, shape, shape);
 }
 
-// layout of one pool type (pool_layout.hpp): ProductTwoCoin gets the bucketed TMA
-// layout of the requested tile shape (the interleaved shape when hubs are
-// detected and the default was asked for); the other types are a-sorted only.
-cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m,
-                            int* variant_used) {
-  const bool product = type == CFMM_POOL_PRODUCT;
-  const int v = product ? ctx->tma_variant : -1;
-  const cfmm::TileShape normal = tile_shape_of(v);
-  const cfmm::TileShape skew = (product && v == 0 && ctx->skew_interleaved) ? tile_shape_of(kSkewVariant) : normal;
-  cfmm::PoolLayout lay = cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree,
-                                                 product, normal, skew);
-  *variant_used = (lay.used_skew_shape && v == 0 && ctx->skew_interleaved) ? kSkewVariant : v;
-  return lay;
-}
+int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s);
 
 int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
   if (s.m == 0) return CFMM_OK;
   const int64_t m = s.m;
-  int variant = -1;
-  cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m, &variant);
+  cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m);
   const std::vector<int>&oa = lay.oa, &ob = lay.ob;
   s.swapped = lay.swapped;
   s.skewed = lay.skewed;
   s.order = lay.order;
   s.m_padded = lay.m_padded;
   s.tma_ok = lay.bucketed;
-  s.tma_variant = variant;
   s.nb = (int)lay.nb;
-  const std::vector<int>& tile_bucket = lay.tile_bucket;
+  s.chunk_bucket = lay.tile_bucket;
+  s.sched_grid = 0;
   const int64_t mp = s.m_padded;
   std::vector<double> gam((size_t)mp, 1.0);
   std::vector<int2> ai((size_t)mp);
@@ -298,7 +255,6 @@ int upload_set(cfmm_ctx* ctx, int type) {
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
   CU_TRY(ctx, s.d_gidx.upload(gidx));
-  if (s.tma_ok) CU_TRY(ctx, s.d_tile_bucket.upload(tile_bucket));
   if (type != CFMM_POOL_UNIV3) {
     std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
     bool ok = true;
@@ -312,6 +268,10 @@ int upload_set(cfmm_ctx* ctx, int type) {
     }
     s.in_fast_range = ok;
     CU_TRY(ctx, s.d_R.upload(r));
+    if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
+      int rc = refresh_scaled_reserves(ctx, s);
+      if (rc != CFMM_OK) return rc;
+    }
   }
   if (type == CFMM_POOL_GEOMEAN) {
     std::vector<double2> w((size_t)m);
@@ -443,91 +403,106 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
-template <int V, bool ECON, int NRED = 0, bool SKEW = false>
+// (Re)build the derived scaled-reserve copy and the per-token scale table of the
+// fixed-point slice (three small kernels, off the hot path: finalize and every
+// reserve mutation).  fixed_ok tells the launcher whether the pool set qualifies.
+int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s) {
+  s.fixed_ok = false;
+  if (!s.tma_ok || s.m_padded == 0) return CFMM_OK;
+  const int64_t mp = s.m_padded;
+  const int n = (int)ctx->n_tokens;
+  cudaStream_t st = ctx->stream;
+  const int threads = 256;
+  const unsigned pblocks = (unsigned)((mp + threads - 1) / threads);
+  if (s.d_ig.n != (size_t)mp) {  // γ never changes after finalize
+    CU_TRY(ctx, s.d_ig.alloc((size_t)mp));
+    cfmm::inv_gamma_kernel<<<pblocks, threads, 0, st>>>(s.d_gam.p, mp, s.d_ig.p);
+    ctx->launches++;
+  }
+  if (s.d_Rs.n != (size_t)mp) CU_TRY(ctx, s.d_Rs.alloc((size_t)mp));
+  if (s.d_inv_scale.n != (size_t)n) CU_TRY(ctx, s.d_inv_scale.alloc((size_t)n));
+  if (s.d_tok_sum.n != (size_t)n + 2) CU_TRY(ctx, s.d_tok_sum.alloc((size_t)n + 2));  // + 2 flag words
+  CU_TRY(ctx, cudaMemsetAsync(s.d_tok_sum.p, 0, ((size_t)n + 2) * sizeof(double), st));
+  int* d_flags = reinterpret_cast<int*>(s.d_tok_sum.p + n);
+  cfmm::token_reserve_sum_kernel<<<pblocks, threads, 0, st>>>(s.d_R.p, s.d_Ai.p, mp, s.d_tok_sum.p);
+  cfmm::token_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+      s.d_tok_sum.p, n, s.d_inv_scale.p, d_flags);
+  cfmm::scaled_reserves_kernel<<<pblocks, threads, 0, st>>>(s.d_R.p, s.d_Ai.p, mp, s.d_tok_sum.p,
+                                                          s.d_inv_scale.p, s.d_Rs.p, d_flags);
+  ctx->launches += 3;
+  int h_flags[4] = {0, 0, 0, 0};
+  CU_TRY(ctx, cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  CU_TRY(ctx, cudaGetLastError());
+  s.fixed_ok = h_flags[0] == 0 && h_flags[1] == 0;
+  return CFMM_OK;
+}
+
+// upload the tile schedule for `grid` CTAs (rebuilt only when the grid or tile size changes)
+int ensure_schedule(cfmm_ctx* ctx, PoolSet& s, int grid) {
+  if (s.sched_grid == grid && s.sched_max_chunks == ctx->tile_chunks) return CFMM_OK;
+  const cfmm::TileSchedule ts = cfmm::build_tile_schedule(s.chunk_bucket, grid, ctx->tile_chunks);
+  static_assert(sizeof(int4) == 4 * sizeof(int), "tile descriptor packing");
+  CU_TRY(ctx, s.d_tile_desc.alloc(ts.desc.size() / 4));
+  CU_TRY(ctx, cudaMemcpy(s.d_tile_desc.p, ts.desc.data(), ts.desc.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(ctx, s.d_cta_tile_start.upload(ts.cta_start));
+  s.sched_grid = grid;
+  s.sched_max_chunks = ctx->tile_chunks;
+  return CFMM_OK;
+}
+
+template <bool ECON, bool SKEW, bool FIXED>
 int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                            cudaStream_t st) {
-  constexpr TmaVariant tv = kTmaVariants[V];
-  using Cfg = cfmm::ProductTmaCfg<tv.threads, tv.L, tv.S, tv.nbmax>;
-  auto kern = cfmm::product_sweep_tma<tv.threads, tv.L, tv.S, tv.nbmax, tv.minb, ECON, NRED, SKEW, tv.seq, tv.bulk,
-                                      tv.warpred>;
+  auto kern = cfmm::product_sweep_tma<ECON, SKEW, FIXED>;
   int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::kSmemBytes));
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tv.threads,
-                                                              Cfg::kSmemBytes));
-    if (occ < 1)
-      return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma variant %d does not fit on an SM", V);
+                                     cfmm::kTmaSmemBytes));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfmm::kTmaThreads,
+                                                              cfmm::kTmaSmemBytes));
+    if (occ < 1) return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma does not fit on an SM");
   }
-  const int n_tiles = (int)(s.m_padded / Cfg::kTile);
+  const int64_t n_chunks = (int64_t)s.chunk_bucket.size();
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
-  if (grid > n_tiles) grid = n_tiles;
+  if (grid > n_chunks) grid = (int)n_chunks;
+  int rc = ensure_schedule(ctx, s, grid);
+  if (rc != CFMM_OK) return rc;
   cfmm::FusedExchange fx = ctx->fx_pending;
   if (fx.mode != 0) {
-    ctx->grid_done_target += (unsigned long long)grid;
-    fx.target = ctx->grid_done_target;
+    fx.target = ctx->grid_done_target + (unsigned long long)grid;
     fx.grid_done = ctx->d_grid_done.p;
     ctx->fx_pending.mode = 0;  // consumed
   }
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
-  kern<<<grid, tv.threads, Cfg::kSmemBytes, st>>>(
-      s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_tile_bucket.p, n_tiles, s.nb, d_v, d_psi,
-      (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0,
-      ctx->exact | (ctx->a_red_per_thread ? 0 : 16), fx);
+  kern<<<grid, cfmm::kTmaThreads, cfmm::kTmaSmemBytes, st>>>(
+      FIXED ? s.d_Rs.p : s.d_R.p, s.d_gam.p, s.d_ig.p, s.d_Ai.p, s.d_tile_desc.p, s.d_cta_tile_start.p, s.nb, d_v,
+      FIXED ? s.d_inv_scale.p : nullptr, d_psi, (int)ctx->n_tokens, take_zero_pending(ctx),
+      s.in_fast_range ? 1 : 0, ctx->exact, fx);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
+  // the grid-barrier target moves only once the launch is known to be accepted
+  if (fx.mode != 0) ctx->grid_done_target = fx.target;
   return CFMM_OK;
 }
 
 int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
                        cudaStream_t st) {
   const bool econ = ctx->gradient_math != 0;
-#define CFMM_TMA_CASE(V)                                                          \
-  case V:                                                                         \
-    return econ ? launch_product_tma_cfg<V, true>(ctx, s, d_v, d_psi, st)         \
-                : launch_product_tma_cfg<V, false>(ctx, s, d_v, d_psi, st);
-  switch (s.tma_variant) {
-    CFMM_TMA_CASE(1)
-    CFMM_TMA_CASE(2)
-    CFMM_TMA_CASE(3)
-    CFMM_TMA_CASE(4)
-    CFMM_TMA_CASE(5)
-    CFMM_TMA_CASE(6)
-    CFMM_TMA_CASE(7)
-    CFMM_TMA_CASE(8)
-    CFMM_TMA_CASE(9)
-    CFMM_TMA_CASE(10)
-    CFMM_TMA_CASE(11)
-    CFMM_TMA_CASE(12)
-    CFMM_TMA_CASE(13)
-    CFMM_TMA_CASE(14)
-    CFMM_TMA_CASE(15)
-    CFMM_TMA_CASE(16)
-    CFMM_TMA_CASE(18)
-    CFMM_TMA_CASE(19)
-    CFMM_TMA_CASE(20)
-    CFMM_TMA_CASE(21)
-    CFMM_TMA_CASE(22)
-    CFMM_TMA_CASE(23)
-    CFMM_TMA_CASE(24)
-    CFMM_TMA_CASE(25)
-    case kSkewVariant:
-      if (s.skewed)  // hub tokens detected at finalize: instantiation with in-warp duplicate combining
-        return econ ? launch_product_tma_cfg<kSkewVariant, true, 0, true>(ctx, s, d_v, d_psi, st)
-                    : launch_product_tma_cfg<kSkewVariant, false, 0, true>(ctx, s, d_v, d_psi, st);
-      if (econ && ctx->b_red_pools == 1) return launch_product_tma_cfg<kSkewVariant, true, 1>(ctx, s, d_v, d_psi, st);
-      if (econ && ctx->b_red_pools == 2) return launch_product_tma_cfg<kSkewVariant, true, 2>(ctx, s, d_v, d_psi, st);
-      return econ ? launch_product_tma_cfg<kSkewVariant, true>(ctx, s, d_v, d_psi, st)
-                  : launch_product_tma_cfg<kSkewVariant, false>(ctx, s, d_v, d_psi, st);
-    default:
-      if (s.skewed)  // hub tokens: the SKEW instantiation of the default (sequential) shape
-        return econ ? launch_product_tma_cfg<0, true, 0, true>(ctx, s, d_v, d_psi, st)
-                    : launch_product_tma_cfg<0, false, 0, true>(ctx, s, d_v, d_psi, st);
-      return econ ? launch_product_tma_cfg<0, true>(ctx, s, d_v, d_psi, st)
-                  : launch_product_tma_cfg<0, false>(ctx, s, d_v, d_psi, st);
-  }
+  const bool fixed = ctx->psi_fixed_point && s.fixed_ok;
+#define CFMM_TMA_CASE(E, K, F) \
+  if (econ == E && s.skewed == K && fixed == F) return launch_product_tma_cfg<E, K, F>(ctx, s, d_v, d_psi, st);
+  CFMM_TMA_CASE(true, false, true)
+  CFMM_TMA_CASE(true, false, false)
+  CFMM_TMA_CASE(true, true, true)
+  CFMM_TMA_CASE(true, true, false)
+  CFMM_TMA_CASE(false, false, true)
+  CFMM_TMA_CASE(false, false, false)
+  CFMM_TMA_CASE(false, true, true)
+  CFMM_TMA_CASE(false, true, false)
 #undef CFMM_TMA_CASE
+  return fail(ctx, CFMM_ERR_INVALID, "unreachable");
 }
 
 // One sweep.  The kernels accumulate into the internal ping-pong accumulator
@@ -913,6 +888,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   d_pos.release();
   if (e != cudaSuccess)
     return fail(ctx, CFMM_ERR_CUDA, "update_reserves failed: %s", cudaGetErrorString(e));
+  if (type == CFMM_POOL_PRODUCT) return refresh_scaled_reserves(ctx, s);
   return CFMM_OK;
 }
 
@@ -945,6 +921,10 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
     flag.release();
     if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "apply_trades failed: %s", cudaGetErrorString(e));
     if (h) s.in_fast_range = false;  // later sweeps take the generic (guarded) form
+    if (t == CFMM_POOL_PRODUCT) {
+      int rc2 = refresh_scaled_reserves(ctx, s);
+      if (rc2 != CFMM_OK) return rc2;
+    }
   }
   return CFMM_OK;
 }
@@ -957,29 +937,25 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (value < 0 || value > 32) return fail(ctx, CFMM_ERR_INVALID, "blocks_per_sm out of range");
     ctx->blocks_per_sm = (int)value;
   } else if (!strcmp(key, "tma_variant")) {
-    if (value < -1 || value >= kNumTmaVariants) return fail(ctx, CFMM_ERR_INVALID, "tma_variant out of range");
+    if (value < -1 || value > 0) return fail(ctx, CFMM_ERR_INVALID, "tma_variant must be 0 (bucketed layout, TMA kernel) or -1");
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "tma_variant fixes the pool layout: set it before cfmm_finalize");
     ctx->tma_variant = (int)value;
-  } else if (!strcmp(key, "skew_interleaved")) {
-    if (ctx->finalized)
-      return fail(ctx, CFMM_ERR_STATE, "skew_interleaved fixes the pool layout: set it before cfmm_finalize");
-    ctx->skew_interleaved = value != 0;
   } else if (!strcmp(key, "orient_by_degree")) {
     if (ctx->finalized)
       return fail(ctx, CFMM_ERR_STATE, "orient_by_degree fixes the pool layout: set it before cfmm_finalize");
     ctx->orient_by_degree = value < 0 ? -1 : (value != 0);
-  } else if (!strcmp(key, "b_red_pools")) {
-    if (value < 0 || value > 7) return fail(ctx, CFMM_ERR_INVALID, "b_red_pools out of range");
-    ctx->b_red_pools = (int)value;
+  } else if (!strcmp(key, "psi_fixed_point")) {
+    ctx->psi_fixed_point = value != 0;
+  } else if (!strcmp(key, "tile_chunks")) {
+    if (value < 1 || value > cfmm::kTmaWarps) return fail(ctx, CFMM_ERR_INVALID, "tile_chunks out of range 1..14");
+    ctx->tile_chunks = (int)value;
   } else if (!strcmp(key, "fused_exchange")) {
     ctx->fused_exchange = value != 0;
   } else if (!strcmp(key, "exchange_two_shot")) {
     ctx->comm.force_mode((int)value);
   } else if (!strcmp(key, "sweep_events")) {
     ctx->sweep_events = value != 0;
-  } else if (!strcmp(key, "a_red_per_thread")) {
-    ctx->a_red_per_thread = value != 0;
   } else if (!strcmp(key, "gradient_math")) {
     ctx->gradient_math = value != 0;
   } else if (!strcmp(key, "geomean_log2")) {
@@ -1053,13 +1029,13 @@ void cfmm_host_free(void* p) {
 }
 
 // Test hook (no CUDA call): the device layout finalize would build for m
-// ProductTwoCoin pools.  info[6] = {m_padded, nb, bucketed, skewed, tile, variant};
-// order_out [cap] (device position -> pool index, -1 = padding), tile_bucket_out
-// [cap / tile], swapped_out [m] are filled when cap >= m_padded (call with cap = 0 first).
+// ProductTwoCoin pools.  info[6] = {m_padded, nb, bucketed, skewed, chunk, variant};
+// order_out [cap] (device position -> pool index, -1 = padding), chunk_bucket_out
+// [cap / chunk], swapped_out [m] are filled when cap >= m_padded (call with cap = 0 first).
 int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t* Ai, int orient,
                               int variant, int64_t cap, int64_t* order_out,
-                              int32_t* tile_bucket_out, uint8_t* swapped_out, int64_t* info) {
-  if (!Ai || !info || m < 0 || n_tokens < 2 || variant < -1 || variant >= kNumTmaVariants)
+                              int32_t* chunk_bucket_out, uint8_t* swapped_out, int64_t* info) {
+  if (!Ai || !info || m < 0 || n_tokens < 2 || variant < -1 || variant > 0)
     return CFMM_ERR_INVALID;
   for (int64_t i = 0; i < 2 * m; ++i)
     if (Ai[i] < 1 || Ai[i] > n_tokens) return CFMM_ERR_INVALID;
@@ -1067,21 +1043,37 @@ int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t* Ai, in
   fake.n_tokens = n_tokens;
   fake.tma_variant = variant;
   fake.orient_by_degree = orient;
-  int used = -1;
-  const cfmm::PoolLayout lay = layout_for(&fake, CFMM_POOL_PRODUCT, Ai, m, &used);
-  const int64_t tile = used >= 0 ? (int64_t)kTmaVariants[used].threads * kTmaVariants[used].L : 0;
+  const cfmm::PoolLayout lay = layout_for(&fake, CFMM_POOL_PRODUCT, Ai, m);
   info[0] = lay.m_padded;
   info[1] = lay.nb;
   info[2] = lay.bucketed;
   info[3] = lay.skewed;
-  info[4] = tile;
-  info[5] = used;
+  info[4] = lay.bucketed ? cfmm::kTmaChunk : 0;
+  info[5] = variant;
   if (cap >= lay.m_padded && order_out) {
     for (int64_t p = 0; p < lay.m_padded; ++p) order_out[p] = lay.order[(size_t)p];
-    if (tile_bucket_out)
-      for (size_t t = 0; t < lay.tile_bucket.size(); ++t) tile_bucket_out[t] = lay.tile_bucket[t];
+    if (chunk_bucket_out)
+      for (size_t t = 0; t < lay.tile_bucket.size(); ++t) chunk_bucket_out[t] = lay.tile_bucket[t];
     if (swapped_out)
       for (int64_t i = 0; i < m; ++i) swapped_out[i] = lay.swapped[(size_t)i];
+  }
+  return CFMM_OK;
+}
+
+// Test hook (no CUDA call): the tile schedule of the TMA kernel for a chunk->bucket map.
+// desc_out [4 * cap_tiles] and cta_start_out [grid + 1] are filled when they are large enough;
+// counts_out[2] = {tiles, grid used}.
+int cfmm_debug_tile_schedule(const int32_t* chunk_bucket, int64_t n_chunks, int grid, int max_chunks,
+                             int64_t cap_tiles, int32_t* desc_out, int32_t* cta_start_out,
+                             int64_t* counts_out) {
+  if (!chunk_bucket || !counts_out || n_chunks < 1 || grid < 1 || max_chunks < 1) return CFMM_ERR_INVALID;
+  const std::vector<int> cb(chunk_bucket, chunk_bucket + n_chunks);
+  const cfmm::TileSchedule ts = cfmm::build_tile_schedule(cb, grid, max_chunks);
+  counts_out[0] = (int64_t)(ts.desc.size() / 4);
+  counts_out[1] = ts.grid;
+  if (desc_out && cta_start_out && cap_tiles >= counts_out[0]) {
+    memcpy(desc_out, ts.desc.data(), ts.desc.size() * sizeof(int));
+    memcpy(cta_start_out, ts.cta_start.data(), ts.cta_start.size() * sizeof(int));
   }
   return CFMM_OK;
 }

@@ -14,16 +14,16 @@
 namespace cfmm {
 
 struct TileShape {
-  int64_t tile = 0;   // pools per tile (threads * L); 0 = no bucketing
+  int64_t tile = 0;   // padding unit in pools (one warp-chunk of the TMA kernel); 0 = no bucketing
   int64_t nbmax = 0;  // capacity of the shared ν / Ψ slices, in tokens
-  int64_t nb_align = 1;  // bucket width is a multiple of this (2: 16-byte bucket bases for bulk reductions)
+  int64_t nb_align = 1;  // bucket width is a multiple of this
 };
 
 struct PoolLayout {
   std::vector<int64_t> order;    // device position -> insertion index within the type, -1 = padding
   std::vector<int> oa, ob;       // device orientation per insertion index (0-based tokens)
   std::vector<uint8_t> swapped;  // per insertion index: stored with its two tokens exchanged
-  std::vector<int> tile_bucket;  // bucket of every tile (bucketed layouts only)
+  std::vector<int> tile_bucket;  // bucket of every chunk (bucketed layouts only)
   int64_t m_padded = 0;
   int64_t nb = 0;                // bucket width in tokens
   bool bucketed = false;
@@ -105,6 +105,42 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     for (int64_t t = start[(size_t)k] / tile; t < start[(size_t)k + 1] / tile; ++t)
       lay.tile_bucket[(size_t)t] = (int)k;
   return lay;
+}
+
+// ---- tile schedule of the TMA kernel ----------------------------------------------
+// The padded device order is a sequence of chunks (one warp's share of a tile);
+// chunk_bucket[c] is non-decreasing.  CTA g of `grid` owns the chunk range
+// [C*g/grid, C*(g+1)/grid) -- balanced to one chunk -- and walks it in tiles of up
+// to `max_chunks` consecutive chunks that never straddle a bucket boundary.
+struct TileSchedule {
+  std::vector<int> desc;       // 4 ints per tile: first chunk, chunk count, bucket, 0
+  std::vector<int> cta_start;  // [grid + 1] tile index ranges
+  int grid = 0;
+};
+
+inline TileSchedule build_tile_schedule(const std::vector<int>& chunk_bucket, int grid, int max_chunks) {
+  TileSchedule ts;
+  const int64_t C = (int64_t)chunk_bucket.size();
+  if (grid > C) grid = (int)C;
+  if (grid < 1) grid = 1;
+  ts.grid = grid;
+  ts.cta_start.assign((size_t)grid + 1, 0);
+  for (int g = 0; g < grid; ++g) {
+    const int64_t lo = C * g / grid, hi = C * (g + 1) / grid;
+    int64_t c = lo;
+    while (c < hi) {
+      const int bk = chunk_bucket[(size_t)c];
+      int64_t e = c + 1;
+      while (e < hi && e - c < max_chunks && chunk_bucket[(size_t)e] == bk) ++e;
+      ts.desc.push_back((int)c);
+      ts.desc.push_back((int)(e - c));
+      ts.desc.push_back(bk);
+      ts.desc.push_back(0);
+      c = e;
+    }
+    ts.cta_start[(size_t)g + 1] = (int)(ts.desc.size() / 4);
+  }
+  return ts;
 }
 
 }  // namespace cfmm

@@ -155,20 +155,26 @@ int cfmm_apply_trades(cfmm_ctx *ctx);
  *                      one rcp; GeometricMean: one pow), <= ~3 ulp of the reserve per pool;
  *                      0 = the reference's operation order, bit-identical per pool.
  *                      Materialising sweeps and "exact" are always bit-identical.
- *   "tma_variant"      tile shape / form of the ProductTwoCoin TMA kernel; fixes the pool
- *                      layout, so it must be set before cfmm_finalize (-1 = none).
+ *   "tma_variant"      0 (default) = b-bucketed ProductTwoCoin layout + TMA kernel for
+ *                      gradient-only sweeps; -1 = token-sorted layout, first-generation
+ *                      kernel only.  Fixes the pool layout: before cfmm_finalize.
+ *   "psi_fixed_point"  Ψ[b] partial sums of the TMA kernel: 1 (default) = 64-bit fixed
+ *                      point on native 32-bit shared atomics (quantum <= 2^-59 of the
+ *                      token's total reserve; used when every token's pools span <= 2^40
+ *                      in reserve and totals lie within 2^+-200), 0 = fp64 CAS adds.
  *   "orient_by_degree" store each ProductTwoCoin pool with its higher-degree token first:
  *                      -1 (default) = only when finalize detects hub tokens, 0 never,
  *                      1 always; before cfmm_finalize.
  *   "use_tma"          0 = run the first-generation kernel on the same layout.
- *   "a_red_per_thread" / "b_red_pools" / "blocks_per_sm"   scatter-path experiments.
+ *   "blocks_per_sm" / "tile_chunks"   grid / tile-size measurement knobs.
  *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
  *                      in the sweep kernel's tail; 0 = separate exchange launch.
  *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol
  *                      (default: two-shot for more than two ranks); after cfmm_comm_attach.
  *   "sweep_events"     0 = do not record the two CUDA events cfmm_last_sweep_ms needs.
- *   "geomean_log2"     staged experiment (not validated on hardware yet): 1 = gradient-only
- *                      GeometricMean sweeps take the power as exp2(e*log2 t) instead of pow.
+ *   "geomean_log2"     gradient-only GeometricMean sweeps take the power as exp2(e*log2 t)
+ *                      (1, default; <= 12 ulp over the admitted range, validated against
+ *                      pow on hardware) or as pow (0).
  *   "profile"          N = time the next N kernel launches (cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
@@ -197,13 +203,20 @@ int cfmm_selftest_inrange_math(cfmm_ctx *ctx, const double *a, const double *b,
                                int64_t n, int64_t *mismatches);
 
 /* Test hook, needs no device: the layout cfmm_finalize would give m ProductTwoCoin
- * pools (Ai 1-based [2m]) for tile shape `variant` and orientation mode `orient`.
- * info[6] = {m_padded, bucket width, bucketed?, hubs detected?, tile size, variant used};
+ * pools (Ai 1-based [2m]) for "tma_variant" `variant` and orientation mode `orient`.
+ * info[6] = {m_padded, bucket width, bucketed?, hubs detected?, chunk size, variant};
  * with cap >= m_padded also order_out [m_padded] (device position -> pool index, -1 =
- * padding), tile_bucket_out [m_padded / tile] and swapped_out [m]. */
+ * padding), chunk_bucket_out [m_padded / chunk] and swapped_out [m]. */
 int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t *Ai, int orient,
                               int variant, int64_t cap, int64_t *order_out,
-                              int32_t *tile_bucket_out, uint8_t *swapped_out, int64_t *info);
+                              int32_t *chunk_bucket_out, uint8_t *swapped_out, int64_t *info);
+/* Test hook, needs no device: the TMA kernel's tile schedule for a chunk -> bucket map
+ * (non-decreasing) on `grid` CTAs with at most max_chunks chunks per tile.
+ * counts_out[2] = {tiles, grid used}; desc_out [4 per tile: first chunk, chunk count,
+ * bucket, 0] and cta_start_out [grid + 1] are filled when cap_tiles >= tiles. */
+int cfmm_debug_tile_schedule(const int32_t *chunk_bucket, int64_t n_chunks, int grid, int max_chunks,
+                             int64_t cap_tiles, int32_t *desc_out, int32_t *cta_start_out,
+                             int64_t *counts_out);
 
 /* ---- pinned host memory helpers ------------------------------------------- */
 void *cfmm_host_alloc(size_t bytes);

@@ -43,13 +43,17 @@ def make_pools(cr, n, product=None, geomean=None, univ3=None, exact=None, pre=No
 EPS = np.finfo(np.float64).eps
 
 
-def check_psi(oracle, Ai, D, L, v, n, psi, acc, R=None, g=None):
+def check_psi(oracle, Ai, D, L, v, n, psi, acc, R=None, g=None, Rq=None):
     """Ψ, acc against an extended-precision pool-order sum of the oracle's
     per-pool trades.  Strict form (R is None): only summation-order noise is
     allowed, 1e-12·Σ(|Λ|+|Δ|)_j per component.  With R, g given (gradient-only
     ProductTwoCoin sweeps in the default economized math) each pool may add up
     to 32 ulp of its reserves: the same order as the rounding of the
-    reference's own expression sqrt(γmk) − R."""
+    reference's own expression sqrt(γmk) − R.  Rq (the reserves; defaults to R):
+    gradient-only sweeps of the TMA kernel accumulate Ψ[b] partials in 64-bit
+    fixed point with a quantum <= 2^-59 of the token's total reserve S_j, so token j
+    may carry deg_j · S_j · 2^-59 of quantisation on top (the integer sum itself
+    is exact and order-independent)."""
     accx, Gx, absG = oracle.fold_compensated(Ai, D, L, v, n)
     ref = Gx.astype(np.float64)
     slack = np.zeros(n)
@@ -57,6 +61,14 @@ def check_psi(oracle, Ai, D, L, v, n, psi, acc, R=None, g=None):
         w = 32 * EPS * (R[:, 0] + R[:, 1]) / g
         np.add.at(slack, Ai[:, 0] - 1, w)
         np.add.at(slack, Ai[:, 1] - 1, w)
+    if Rq is None:
+        Rq = R
+    if Rq is not None:
+        S, deg = np.zeros(n), np.zeros(n)
+        for side in (0, 1):
+            np.add.at(S, Ai[:len(Rq), side] - 1, np.abs(Rq[:, side]))
+            np.add.at(deg, Ai[:len(Rq), side] - 1, 1.0)
+        slack = slack + deg * S * 2.0 ** -59
     # north_star tolerance: 1e-6 relative (norm-wise); the rounding floor of the sums
     # themselves is added so that a Ψ that is zero up to noise (pools already at their
     # no-arbitrage point) does not turn the relative test into noise / noise
@@ -146,7 +158,11 @@ def test_product_sweep_parity(cr, oracle, synth, m, n, kind, exact):
     # ... and the reference operation order (only summation-order noise)
     p.set_option("gradient_math", 0)
     psi3, acc3 = p.sweep(v, materialize=False)
-    check_psi(oracle, Ai, Do, Lo, v, n, psi3, acc3)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi3, acc3, Rq=R)
+    # ... and with fp64 (CAS) slice partials instead of fixed point: strictly summation noise
+    p.set_option("psi_fixed_point", 0)
+    psi4, acc4 = p.sweep(v, materialize=False)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi4, acc4)
     p.close()
 
 
@@ -264,13 +280,17 @@ def test_inrange_math(cr):
     p.close()
 
 
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15])
-@pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7)])
-def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
-    """Every tile shape of the b-bucketed TMA kernel (several buckets at
-    n = 20011, one bucket at n = 7), and the first-generation kernel (-1)."""
+@pytest.mark.parametrize("variant,fixed,chunks", [(-1, 1, 14), (0, 1, 14), (0, 0, 14), (0, 1, 5), (0, 0, 1)])
+@pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7), (96, 2), (97, 1601)])
+def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, chunks, m, n):
+    """The b-bucketed TMA kernel with fixed-point and with fp64 slice partials, with
+    full and with short tiles (several buckets at n = 20011, one bucket at n = 7,
+    a single chunk, a chunk plus one pool in a second bucket), and the
+    first-generation kernel (-1)."""
     R, g, Ai = synth.product_pools(m, n, seed=variant + 10)
     p = make_pools(cr, n, product=(R, g, Ai), pre={"tma_variant": variant})
+    p.set_option("psi_fixed_point", fixed)
+    p.set_option("tile_chunks", chunks)
     for kind in ("near", "wide"):
         v = synth.dual_prices(n, kind)
         Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
@@ -279,7 +299,7 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
         check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)
         p.set_option("gradient_math", 0)
         psi, acc = p.sweep(v)
-        check_psi(oracle, Ai, Do, Lo, v, n, psi, acc)
+        check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, Rq=R if fixed else None)
     # same layout, first-generation kernel
     p.set_option("use_tma", 0)
     psi, acc = p.sweep(v)
@@ -293,6 +313,37 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, m, n):
     p.close()
 
 
+def test_fixed_point_slice_rules(cr, oracle, synth):
+    """The fixed-point slice is used only when every token's pools span <= 2^40 in
+    reserve; a pool set that violates the rule silently takes the fp64 slice, and a
+    reserve push that repairs it switches back.  Oversized tenders (|flow| > 4 R2) and
+    NaN leave the integer path through a global fp64 RED.  Checked through results
+    only: Ψ must match the oracle in every state."""
+    m, n = 120_000, 2_000
+    R, g, Ai = synth.product_pools(m, n, seed=9)
+    R[5] = [3.0e-9, 2.0e-9]                    # 2^40 below its tokens' totals (~1e5)
+    v = synth.dual_prices(n, "wide")
+    p = make_pools(cr, n, product=(R, g, Ai))
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    psi, acc = p.sweep(v)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g, Rq=np.zeros_like(R))  # fp64 slice: no quantisation
+    R[5] = [30.0, 20.0]
+    p.update_reserves(0, 5, R[5:6])
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    psi, acc = p.sweep(v)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)
+    # prices 1e6 apart: most pools tender far more than 4x their reserve
+    v2 = v.copy()
+    v2[::2] *= 1.0e6
+    Do, Lo = oracle.sweep_product(R, g, Ai, v2, threads=8)
+    psi, acc = p.sweep(v2)
+    check_psi(oracle, Ai, Do, Lo, v2, n, psi, acc, R=R * 1e4, g=g)
+    p.set_option("gradient_math", 0)
+    psi, acc = p.sweep(v2)
+    check_psi(oracle, Ai, Do, Lo, v2, n, psi, acc, Rq=R)
+    p.close()
+
+
 @pytest.mark.parametrize("orient", [-1, 1, 0])
 def test_skewed_token_graph(cr, oracle, synth, orient):
     """Zipf-distributed tokens (hubs on either side of many pools): per-pool
@@ -301,7 +352,7 @@ def test_skewed_token_graph(cr, oracle, synth, orient):
     m, n = 200_000, 5_000
     R, g, Ai = synth.product_pools_skewed(m, n, alpha=1.0, seed=77)
     v = synth.dual_prices(n, "wide")
-    p = make_pools(cr, n, product=(R, g, Ai), pre={"orient_by_degree": orient, "skew_interleaved": int(orient == 1)})
+    p = make_pools(cr, n, product=(R, g, Ai), pre={"orient_by_degree": orient})
     Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
     psi, acc = p.sweep(v)
     check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)
@@ -591,7 +642,7 @@ def test_random_operation_sequences(cr, oracle, synth, seed):
     if mg_ == 0:
         Rg, gg, Ag, wg = Rg[:0], gg[:0], Ag[:0], wg[:0]
     p = cr.DevicePools(n)
-    p.set_option("tma_variant", int(rng.choice([0, 0, 17, 10, -1])))
+    p.set_option("tma_variant", int(rng.choice([0, 0, 0, -1])))
     p.add_product(R, g, Ai)
     if mg_:
         p.add_geomean(Rg, gg, Ag, wg)
@@ -638,7 +689,7 @@ def test_random_operation_sequences(cr, oracle, synth, seed):
                 Rg = Rg + gg[:, None] * D[mp_:] - L[mp_:]
             last_mat = None
         elif op == "toggle":
-            p.set_option(str(rng.choice(["gradient_math", "use_tma", "a_red_per_thread"])), int(rng.integers(0, 2)))
+            p.set_option(str(rng.choice(["gradient_math", "use_tma", "psi_fixed_point"])), int(rng.integers(0, 2)))
     p.close()
 
 
@@ -680,7 +731,7 @@ def test_full_size_config5_10M_pools(cr, oracle, synth):
     check_psi(oracle, Ai, Do, Lo, v, n, psi2, acc2, R=R, g=g)
     p.set_option("gradient_math", 0)
     psi3, acc3 = p.sweep(v)
-    check_psi(oracle, Ai, Do, Lo, v, n, psi3, acc3)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi3, acc3, Rq=R)
     # invariant: every pool's trade keeps ϕ(R+γΔ−Λ) ≥ ϕ(R) − sqrt(eps) (test/arb.jl:11)
     Rp = R + g[:, None] * D - L
     assert np.all(Rp[:, 0] * Rp[:, 1] >= R[:, 0] * R[:, 1] - np.sqrt(np.finfo(float).eps))

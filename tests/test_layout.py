@@ -1,7 +1,8 @@
 """CPU tests of the device layout cfmm_finalize builds for ProductTwoCoin pools
 (csrc/pool_layout.hpp), through the device-free hook cfmm_debug_product_layout:
-b-bucketing, per-bucket padding to whole tiles, a-order inside buckets, hub
-detection and degree orientation."""
+b-bucketing, per-bucket padding to whole 96-pool chunks, a-order inside buckets,
+hub detection and degree orientation; and of the TMA kernel's tile schedule
+(cfmm_debug_tile_schedule): chunk-balanced CTA ranges, tiles inside one bucket."""
 import ctypes as C
 
 import numpy as np
@@ -60,7 +61,7 @@ def check_invariants(Ai, n, lay):
     assert lay["m_padded"] - m < len(np.unique(lay["tile_bucket"])) * tile  # < one tile of padding per bucket
 
 
-@pytest.mark.parametrize("variant", [0, 17, 10, 1])
+@pytest.mark.parametrize("variant", [0, -1])
 @pytest.mark.parametrize("m,n", [(1, 2), (7, 3), (5000, 7), (40_000, 3001), (60_000, 20_011)])
 def test_uniform_graph_layout(cr, m, n, variant):
     from cfmmrouter_b200 import synth
@@ -68,24 +69,47 @@ def test_uniform_graph_layout(cr, m, n, variant):
     lay = layout(cr, n, Ai, variant=variant)
     assert not lay["skewed"] and not lay["swapped"].any() and lay["variant"] == variant
     check_invariants(Ai, n, lay)
-    if m >= 40_000:
-        assert lay["bucketed"]
+    if variant == -1:
+        assert not lay["bucketed"]
+    else:
+        assert lay["bucketed"] and lay["tile"] == 96
+        B = -(-n // 1600)
+        assert lay["nb"] == -(-n // B) and lay["nb"] <= 1600
 
 
-@pytest.mark.parametrize("m,n", [(40_000, 3001), (60_000, 20_011), (100_000, 50_000), (30_000, 1599)])
-def test_bulk_flush_variant_has_even_buckets(cr, m, n):
-    """Variant 23 flushes a bucket's Ψ[b] slice with one 16-byte-granular bulk
-    reduction: its bucket width (hence every bucket base) must be even, still
-    within the 1600-token slice; the default variant's layout is not touched."""
-    from cfmmrouter_b200 import synth
-    _, _, Ai = synth.product_pools(m, n, seed=m + n)
-    lay = layout(cr, n, Ai, variant=23)
-    check_invariants(Ai, n, lay)
-    assert lay["bucketed"] and lay["nb"] % 2 == 0 and lay["nb"] <= 1600
-    ref = layout(cr, n, Ai, variant=0)
-    B = -(-n // 1600)
-    assert ref["nb"] == -(-n // B)          # unchanged rule for the validated variant
-    assert lay["nb"] in (ref["nb"], ref["nb"] + 1)
+def schedule(cr, chunk_bucket, grid, max_chunks=14):
+    lib = cr.load_library()
+    cb = np.ascontiguousarray(chunk_bucket, dtype=np.int32)
+    counts = np.zeros(2, dtype=np.int64)
+    i32, i64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    assert lib.cfmm_debug_tile_schedule(cb.ctypes.data_as(i32), len(cb), grid, max_chunks, 0, None, None,
+                                        counts.ctypes.data_as(i64)) == 0
+    tiles, g = int(counts[0]), int(counts[1])
+    desc = np.zeros((tiles, 4), dtype=np.int32)
+    start = np.zeros(g + 1, dtype=np.int32)
+    assert lib.cfmm_debug_tile_schedule(cb.ctypes.data_as(i32), len(cb), grid, max_chunks, tiles,
+                                        desc.ctypes.data_as(i32), start.ctypes.data_as(i32),
+                                        counts.ctypes.data_as(i64)) == 0
+    return desc, start, g
+
+
+@pytest.mark.parametrize("grid", [1, 3, 296, 5000])
+@pytest.mark.parametrize("sizes", [[1], [5, 1, 1, 40], [1000, 3, 2500, 17, 17, 900], [13021] * 8])
+def test_tile_schedule(cr, sizes, grid):
+    cb = np.repeat(np.arange(len(sizes)), sizes)
+    desc, start, g = schedule(cr, cb, grid)
+    C_ = len(cb)
+    assert g == min(grid, C_) and start[0] == 0 and start[-1] == len(desc)
+    assert np.all(np.diff(start) >= 1)                       # every CTA has work
+    first, cnt, bk = desc[:, 0], desc[:, 1], desc[:, 2]
+    assert first[0] == 0 and np.all(first[1:] == first[:-1] + cnt[:-1]) and first[-1] + cnt[-1] == C_
+    assert np.all((cnt >= 1) & (cnt <= 14))
+    for f, c, b in desc[:, :3]:
+        assert np.all(cb[f:f + c] == b)                      # a tile lies in one bucket
+    per_cta = np.array([cnt[start[i]:start[i + 1]].sum() for i in range(g)])
+    assert per_cta.max() - per_cta.min() <= 1                # balanced to one chunk
+    lo = np.array([first[start[i]] for i in range(g)])
+    assert np.array_equal(lo, (C_ * np.arange(g)) // g)
 
 
 def test_sparse_buckets_fall_back_to_a_sorted(cr):
