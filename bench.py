@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--exact", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped)")
+    ap.add_argument("--no-flush", action="store_true", help="small workloads: L2-warm timing only")
+    ap.add_argument("--verify", type=int, default=1, help="N > 1: check the reduced [Psi; acc] (outside the timed regions)")
+    ap.add_argument("--strong", type=int, default=1, help="N > 1 (weak): also time the same total pool count split over the ranks")
     return ap.parse_args()
 
 
@@ -216,8 +219,9 @@ def run_reference(args):
         half_rate, _, _ = cpu_faithful_rate(args.workload, 200_000, 2, threads // 2)
         if half_rate > probe_rate:
             threads, probe_rate = threads // 2, half_rate
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    sample = int(max(10_000, min(m, 2_000_000, probe_rate * budget)))
+    # the whole workload per step when the run still ends within ~3 minutes, else a bounded sample
+    budget = 180.0 / max(1, args.steps + args.warmup)
+    sample = int(max(10_000, min(m, probe_rate * budget)))
     from cfmmrouter_b200 import synth
     f = o.faithful(n)
     R, g, Ai = synth.product_pools(sample, n)
@@ -236,7 +240,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "pools_per_step_sample": sample, "n_tokens": n,
+        "config": {"workload": args.workload, "pools_per_step_sample": sample, "pools_total": m,
+                   "sample_is_whole_workload": sample == m, "n_tokens": n,
                    "note": "reference = CFMMRouter.jl's CPU algorithm; Julia is not installed, so this is "
                            "the oracle's faithful-layout C restatement (threaded sweep, serial folds)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
@@ -271,18 +276,29 @@ def run_ours(args):
     shard = make_shard(args.workload, rank, world, args.scaling)
     n = shard["n"]
     pools = cr.DevicePools(n, device=local_rank)
+    t_ing0 = time.perf_counter()
     if "product" in shard:
         pools.add_product(*shard["product"])
     if "geomean" in shard:
         pools.add_geomean(*shard["geomean"])
     if "univ3" in shard:
         pools.add_univ3(*shard["univ3"])
-    pools.finalize()
+    t_ing1 = time.perf_counter()
+    pools.finalize()  # validate-free part: orientation, (bucket(b), a) sort, SoA gather, upload, scale table
+    t_ing2 = time.perf_counter()
+    ingest = {"pools": shard["m_local"], "add_s": t_ing1 - t_ing0, "finalize_s": t_ing2 - t_ing1,
+              "host_threads": os.cpu_count(),
+              "note": "cfmm_add_* (validation + staging copy) and cfmm_finalize (layout on the host cores with "
+                      "OpenMP, upload, device-side scale table) wall time on this rank"}
     pools.set_option("exact", args.exact)
     pools.set_option("sweep_events", 0)
     m_local = shard["m_local"]
     alg_bytes = float(shard["bytes"])
-    del shard
+    # working sets that fit in the 126 MB L2 are timed with an L2 flush before every step
+    # (value, roofline) AND warm (reported beside it); larger ones stream from HBM anyway
+    flushed = alg_bytes <= 126e6 and not args.no_flush
+    if not (world > 1 and args.verify):
+        shard = None
 
     exchange = "none"
     if world > 1:
@@ -307,13 +323,18 @@ def run_ours(args):
     d_psi = torch.zeros(n + 1, dtype=torch.float64, device=dev)
     stream = torch.cuda.Stream(device=dev)
     sptr = stream.cuda_stream
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flushed else None
 
-    def step():
-        if exchange == "nccl":  # NCCL needs the partial in a torch tensor
-            pools.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, sptr)
-            dist.all_reduce(d_psi)
-        else:  # zero-copy: [Ψ; acc] stays in the context's device buffer
-            pools.sweep_device_view(d_nu.data_ptr(), False, sptr)
+    def make_step(p):
+        def step():
+            if exchange == "nccl":  # NCCL needs the partial in a torch tensor
+                p.sweep_device(d_nu.data_ptr(), d_psi.data_ptr(), False, sptr)
+                dist.all_reduce(d_psi)
+            else:  # zero-copy: [Ψ; acc] stays in the context's device buffer
+                p.sweep_device_view(d_nu.data_ptr(), False, sptr)
+        return step
+
+    step = make_step(pools)
 
     def barrier():
         if world > 1:
@@ -322,18 +343,34 @@ def run_ours(args):
 
     sampler_ref = [None]
 
-    def timed_region(steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed_region(steps, fn=None, flush=False):
+        """ms of `steps` steps on the stream (CUDA events, barrier + synchronize on both sides).
+        flush: write a 256 MB buffer (> L2) before every step and time each step with its own
+        event pair, so the flush itself is outside the timed intervals."""
+        fn = fn or step
         barrier()
+        if flush:
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a, b in ev:
+                flush_buf.zero_()
+                a.record(stream)
+                fn()
+                b.record(stream)
+            if sampler_ref[0] is not None:
+                sampler_ref[0]._sample_once()
+            barrier()
+            return float(sum(a.elapsed_time(b) for a, b in ev))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
-            step()
+            fn()
         e1.record(stream)
         if sampler_ref[0] is not None:
             sampler_ref[0]._sample_once()  # GPU still busy with the queued steps
         barrier()
         return e0.elapsed_time(e1)
 
+    extra = {}
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup)):
             step()
@@ -343,15 +380,24 @@ def run_ours(args):
         sampler = ClockSampler(local_rank)
         sampler_ref[0] = sampler if sampler._nvml else None
         sampler.start()
-        ms_total = timed_region(args.steps)
+        ms_total = timed_region(args.steps, flush=flushed)
+        launches = pools.launch_count - l0
+        # a driver-sized K can be a millisecond of GPU time: also a region of >= 50 ms of the
+        # same steps (`sustained`), so that the clocks are sampled under load
+        if ms_total < 50.0 and not flushed:
+            k2 = int(min(50_000, max(args.steps, np.ceil(60.0 * args.steps / max(ms_total, 1e-3)))))
+            ms2 = timed_region(k2)
+            extra["sustained"] = {"steps": k2, "ms_per_step": ms2 / k2}
         sampler.stop()
         sampler_ref[0] = None
-        launches = pools.launch_count - l0
+        if flushed:
+            ms_warm = timed_region(args.steps)
+            extra["l2_warm"] = {"steps": args.steps, "ms_per_step": ms_warm / args.steps}
         # ---- timed region 2: the same K steps with a CUDA-event pair around every
         # kernel launch (on the launching stream) -> per-kernel durations for `roofline`
         n_kernels = 2 if args.workload.startswith("config3") else 1
         pools.set_option("profile", args.steps * (n_kernels + (1 if exchange == "peer" else 0)))
-        timed_region(args.steps)
+        timed_region(args.steps, flush=flushed)
         prof = {t: pools.profile_read(t) for t in (0, 1, 2, 3)}
         prof_times = {t: pools.profile_times(t) for t in (0, 1, 2)}
         pools.set_option("profile", 0)
@@ -374,6 +420,18 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
 
+        # ---- N > 1, outside every timed region: is the reduced [Ψ; acc] right? --------------
+        if world > 1 and args.verify and exchange == "peer":
+            extra["parity_checked"], extra["parity"] = verify_reduction(
+                torch, dist, pools, shard, nu_host, d_nu, sptr, n, dev, rank, world)
+            shard = None
+        # ---- N > 1: the same TOTAL pool count split over the ranks (BASELINE configs[4] as
+        # written: "10M pools pool-sharded across 8 GPUs") next to the weak-scaling value ------
+        if world > 1 and args.scaling == "weak" and args.strong and exchange == "peer" \
+                and WORKLOADS[args.workload][2] == "product":
+            extra["strong"] = strong_scaling_run(torch, dist, cr, args, pools, make_step, timed_region, barrier,
+                                                 rank, world, local_rank, dev)
+
     # max over ranks
     if world > 1:
         t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
@@ -386,6 +444,13 @@ def run_ours(args):
         total_pools = int(tp.item())
     value = total_pools * args.steps / (ms_total * 1e-3)
     e2e_value = total_pools * e2e_steps / e2e_s
+    for key in ("sustained", "l2_warm"):
+        if key in extra:
+            t = torch.tensor([extra[key]["ms_per_step"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            extra[key]["ms_per_step"] = t.item()
+            extra[key]["value"] = total_pools / (t.item() * 1e-3)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -396,7 +461,7 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kind = WORKLOADS[args.workload][2]
         roofline = roofline_object(prof, prof_times, ms_total, args.steps, launches, kind, m_local,
-                                   alg_bytes, peak, peak_src, read_traffic())
+                                   alg_bytes, peak, peak_src, args.workload, flushed)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -415,7 +480,8 @@ def run_ours(args):
             "config": {"workload": args.workload, "pools_per_gpu": m_local, "pools_total": total_pools,
                        "n_tokens": n, "nu": args.nu, "exact_mode": args.exact, "exchange": exchange,
                        "l2": "inputs larger than L2 (320 MB/GPU > 126 MB)" if alg_bytes > 126e6
-                             else "L2-WARM: working set fits in L2, no flush between steps"},
+                             else ("L2 flushed (256 MB written) before every timed step; the warm figure is in l2_warm"
+                                   if flushed else "L2-WARM: working set fits in L2, no flush between steps")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
                     "d2h_bytes_per_step": 8 * (n + 1), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cfmm_sweep (C ABI), pinned host buffers"},
@@ -424,14 +490,125 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        line["ingest"] = ingest
+        line.update(extra)
         emit(line)
     pools.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _view(torch, ptr, count, dev):
+    class _H:
+        pass
+    h = _H()
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=dev)
+
+
+def verify_reduction(torch, dist, pools, shard, nu_host, d_nu, sptr, n, dev, rank, world):
+    """(1) every rank's partial [Ψ; acc] (option exchange_bypass) against the CPU oracle on that
+    rank's own pools; (2) the peer-exchanged vector == the sum of the partials (NCCL all_reduce
+    of the same partials) within summation-order noise; (3) the exchanged vector is bitwise
+    identical on every rank."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    o = oracle_lib.load()
+    res = {}
+    ptr = pools.sweep_device_view(d_nu.data_ptr(), False, sptr)
+    torch.cuda.synchronize()
+    reduced = _view(torch, ptr, n + 1, dev).clone()
+    pools.set_option("exchange_bypass", 1)
+    ptr = pools.sweep_device_view(d_nu.data_ptr(), False, sptr)
+    torch.cuda.synchronize()
+    partial = _view(torch, ptr, n + 1, dev).clone()
+    pools.set_option("exchange_bypass", 0)
+    dist.barrier()
+    # (1) partial vs oracle on this rank's pools (ProductTwoCoin shards; mixed/univ3: skipped)
+    ok1 = True
+    if shard is not None and "product" in shard and "geomean" not in shard:
+        R, g, Ai = shard["product"]
+        threads = max(1, (os.cpu_count() or 1) // world)
+        D, L = o.sweep_product(R, g, Ai, nu_host, threads=threads)
+        accx, Gx, absG = o.fold_compensated(Ai, D, L, nu_host, n)
+        eps = np.finfo(np.float64).eps
+        slack, S, deg = np.zeros(n), np.zeros(n), np.zeros(n)
+        for side in (0, 1):
+            np.add.at(slack, Ai[:, side] - 1, 32 * eps * (R[:, 0] + R[:, 1]) / g)  # economized math
+            np.add.at(S, Ai[:, side] - 1, R[:, side])
+            np.add.at(deg, Ai[:, side] - 1, 1.0)
+        slack += deg * S * 2.0 ** -53  # fixed-point slice quantum
+        h = partial.cpu().numpy()
+        err = np.abs(h[:n] - Gx.astype(np.float64))
+        ok1 = bool(np.all(err <= 1e-12 * absG + slack))
+        ok1 &= abs(h[n] - float(accx)) <= 1e-12 * float(np.sum(absG * nu_host)) + float(np.sum(slack * nu_host))
+        res["partial_vs_oracle_max_err_over_tol"] = float(np.max(err / (1e-12 * absG + slack + 1e-300)))
+    # (2) exchanged vector vs NCCL sum of the partials
+    total = partial.clone()
+    dist.all_reduce(total)
+    mag = partial.abs()
+    dist.all_reduce(mag)
+    diff = (reduced - total).abs()
+    ok2 = bool(torch.all(diff <= 1e-13 * mag + 1e-300).item())
+    res["exchange_vs_nccl_max_rel"] = float((diff / (mag + 1e-300)).max().item())
+    # (3) bitwise identical on every rank
+    bits = reduced.view(torch.int64)
+    lo, hi = bits.clone(), bits.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok3 = bool(torch.equal(lo, hi))
+    flag = torch.tensor([1 if (ok1 and ok2 and ok3) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res.update({"partial_vs_oracle": ok1, "exchange_equals_sum": ok2, "bitwise_identical_across_ranks": ok3})
+    return bool(flag.item() == 1), res
+
+
+def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_region, barrier, rank, world,
+                       local_rank, dev):
+    """The workload's pool count split over the ranks (strong scaling), timed like `value`, plus
+    the single-GPU time of the same pools (rank 0's weak shard IS that pool set, swept with the
+    exchange bypassed) so that the line carries its own speed-up."""
+    from cfmmrouter_b200 import synth
+    m, n, _ = WORKLOADS[args.workload]
+    lo, hi = (m * rank) // world, (m * (rank + 1)) // world
+    R, g, Ai = synth.product_pools(m, n, seed=1234)
+    ps = cr.DevicePools(n, device=local_rank)
+    ps.add_product(R[lo:hi], g[lo:hi], Ai[lo:hi])
+    del R, g, Ai
+    ps.finalize()
+    ps.set_option("sweep_events", 0)
+    ps.attach_group(dist.group.WORLD)
+    if args.two_shot >= 0:
+        ps.set_option("exchange_two_shot", args.two_shot)
+    fn = make_step(ps)
+    steps = max(args.steps, 200)
+    for _ in range(10):
+        fn()
+    ms = timed_region(steps, fn)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # single GPU, same 10M pools: every rank sweeps its weak shard without the exchange; rank 0's is seed 1234
+    pools_weak.set_option("exchange_bypass", 1)
+    fn1 = make_step(pools_weak)
+    for _ in range(5):
+        fn1()
+    ms1 = timed_region(steps, fn1)
+    pools_weak.set_option("exchange_bypass", 0)
+    t1 = torch.tensor([ms1 if rank == 0 else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    ms1 = t1.item()
+    barrier()
+    ps.close()
+    return {"pools_total": m, "pools_per_gpu": hi - lo, "steps": steps, "us_per_step": 1e3 * ms / steps,
+            "value": m * steps / (ms * 1e-3), "unit": UNIT,
+            "single_gpu_us_per_step": 1e3 * ms1 / steps, "speedup_vs_single_gpu": ms1 / ms,
+            "note": "same total pools split over the ranks (BASELINE configs[4] as written); single_gpu = "
+                    "rank 0 sweeping all of them alone, in the same run"}
+
+
 def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, alg_bytes, peak, peak_src,
-                    traffic):
+                    workload, flushed):
     """The `roofline` object of the JSON line, from the event-bracketed launches of timed
     region 2.  prof[t] = (total_ms, launches) and prof_times[t] = per-launch ms for pool type
     t (3 = peer exchange); ms_total / launches belong to timed region 1 (no events between
@@ -441,6 +618,7 @@ def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, 
     dom_ms, dom_cnt = prof[dom]
     dom_name = {0: "product_sweep_tma (ProductTwoCoin gradient sweep)", 1: "sweep_kernel<GeomeanPools>",
                 2: "sweep_kernel<Univ3Pools>"}[dom]
+    traffic = read_traffic(workload, {0: "product_sweep_tma", 1: "sweep_kernel_geomean", 2: "sweep_kernel_univ3"}[dom])
     if kind == "mixed":
         dom_bytes = (m_local // 2) * (32 if dom == 0 else 48)
     else:
@@ -451,6 +629,7 @@ def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, 
         "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": 1e3 * dom_ms / max(dom_cnt, 1),
         "launches_timed": dom_cnt, "traffic": traffic,
+        "l2_state": "flushed before every timed launch" if flushed else "inputs larger than L2",
     }
     if len(prof_times[dom]):
         # spread of the individual event-bracketed launches: `avg_launch_us` is their mean
@@ -475,14 +654,17 @@ def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, 
 
 
 
-def read_traffic():
-    """dram bytes (read+write) per launch of the dominant kernel from the
-    committed ncu --set full capture, if present (profiles/traffic.json)."""
+def read_traffic(workload, kernel_key):
+    """dram bytes (read+write) per launch of the dominant kernel from the committed
+    ncu --set full capture (profiles/traffic.json) -- only when that capture was taken on THIS
+    workload and kernel; otherwise null (a constant from another run is not a measurement)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             with open(p) as f:
-                return json.load(f).get("dram_bytes_per_launch")
+                for entry in json.load(f).get("captures", []):
+                    if entry.get("workload") == workload and entry.get("kernel_key") == kernel_key:
+                        return entry.get("dram_bytes_per_launch")
         except Exception:
             return None
     return None

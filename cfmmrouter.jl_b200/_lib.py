@@ -37,6 +37,9 @@ SYMBOLS = {
     "cfmm_add_product": (C.c_int, [_ctx, C.c_int64, _dp, _dp, _ip]),
     "cfmm_add_geomean": (C.c_int, [_ctx, C.c_int64, _dp, _dp, _ip, _dp]),
     "cfmm_add_univ3": (C.c_int, [_ctx, C.c_int64, _dp, _dp, _ip, _ip, _dp, _dp]),
+    "cfmm_pool_file_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int64, C.c_int64, _dp, _dp, _ip, _dp]),
+    "cfmm_pool_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), _ip, _ip]),
+    "cfmm_add_pool_file": (C.c_int, [_ctx, C.c_char_p]),
     "cfmm_finalize": (C.c_int, [_ctx]),
     "cfmm_num_pools": (C.c_int64, [_ctx]),
     "cfmm_num_tokens": (C.c_int64, [_ctx]),
@@ -55,8 +58,7 @@ SYMBOLS = {
     "cfmm_selftest_inrange_math": (C.c_int, [_ctx, _dp, _dp, C.c_int64, _ip]),
     "cfmm_debug_product_layout": (C.c_int, [C.c_int64, C.c_int64, _ip, C.c_int, C.c_int, C.c_int64, _ip,
                                           C.POINTER(C.c_int32), C.POINTER(C.c_uint8), _ip]),
-    "cfmm_debug_tile_schedule": (C.c_int, [C.POINTER(C.c_int32), C.c_int64, C.c_int, C.c_int, C.c_int64,
-                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), _ip]),
+    "cfmm_debug_read_trace": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.c_int64, _ip]),
     "cfmm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cfmm_host_free": (None, [C.c_void_p]),
     "cfmm_comm_export": (C.c_int, [_ctx, C.c_void_p]),

@@ -5,6 +5,10 @@
 // There is deliberately no CPU fallback in this file: every compute entry
 // point needs a CUDA device and fails with CFMM_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -75,25 +79,22 @@ struct PoolSet {
   bool in_fast_range = false;  // every R, γ in [2^-100, 2^100] and γ <= 1
   bool tma_ok = false;         // b-bucketed layout built (product only)
   int nb = 0;                  // bucket width in tokens
-  std::vector<int> chunk_bucket;  // product: bucket of every chunk of the padded device order
-  DevBuf<int4> d_tile_desc;    // product: tile schedule of the TMA kernel (pool_layout.hpp) ...
-  DevBuf<int> d_cta_tile_start;  // ... and each CTA's tile range
-  int sched_grid = 0;          // grid the uploaded schedule was built for (0 = none yet)
-  int sched_max_chunks = 0;
-  // fixed-point Ψ[b] slice (product_tma.cuh): derived copy of the reserves with the
-  // second component scaled by 2^s_b, and the per-token 2^-s_b table
-  DevBuf<double2> d_Rs;
+  int64_t n_chunks = 0;        // product: 96-pool chunks of the padded device order
+  cfmm::BucketTable buckets;   // product: first chunk of every b-bucket (travels as a kernel parameter)
+  // derived data of the TMA gradient kernel (product_tma.cuh): the chunk-blocked packed
+  // stream (built lazily for the mode a sweep asks for) and the per-token 2^-s_b table of
+  // the fixed-point Ψ[b] slice
+  DevBuf<unsigned char> d_packed;
+  int packed_mode = -1;        // -1 = stale; else (econ ? 1 : 0) | (fixed ? 2 : 0)
   DevBuf<double> d_inv_scale, d_tok_sum;
-  DevBuf<double> d_ig;         // 1/γ per pool (device order), streamed by the economized gradient sweep
-  bool fixed_ok = false;       // the scaled copy is valid and every token fits the fixed-point rules
+  bool fixed_ok = false;       // every token fits the fixed-point rules (range, totals)
   std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
     d_Ai.release(); d_tick.release(); d_gidx.release();
-    d_tile_desc.release(); d_cta_tile_start.release();
-    d_Rs.release(); d_inv_scale.release(); d_tok_sum.release(); d_ig.release();
+    d_packed.release(); d_inv_scale.release(); d_tok_sum.release();
   }
 };
 
@@ -118,8 +119,8 @@ struct cfmm_ctx {
   int use_tma = 1;     // 0: run the first-generation kernel even when the layout exists
   int orient_by_degree = -1; // ProductTwoCoin: store each pool with its higher-degree token first: -1 auto (skewed graphs only), 0 never, 1 always (fixed at finalize)
   int psi_fixed_point = 1;   // Ψ[b] partials of the TMA kernel: 1 = 64-bit fixed point on native shared atomics when the pool set allows it, 0 = fp64 CAS adds
-  int tile_chunks = cfmm::kTmaWarps;  // chunks per tile of the schedule (<= 14; measurement knob)
-  int sweep_events = 1;      // record ev0/ev1 around every sweep (cfmm_last_sweep_ms)
+  int sweep_events = 0;      // 1 = record ev0/ev1 around every sweep (cfmm_last_sweep_ms); disables the sweep graphs
+  bool events_recorded = false;
   int geomean_log2 = 1;   // gradient-only GeometricMean sweeps: power through exp2/log2 (1, default) or pow (0)
   int gradient_math = 1;  // gradient-only ProductTwoCoin sweeps: 1 = economized (few-ulp), 0 = reference order (bit-identical per pool)
   unsigned long long epoch = 0;  // sweeps enqueued so far
@@ -128,8 +129,31 @@ struct cfmm_ctx {
   DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
+  int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived
+  DevBuf<unsigned long long> d_trace;  // option "trace": per-CTA phase timestamps of the last TMA sweep
+  int trace_grid = 0;
+  // cfmm_sweep as ONE graph launch {H2D ν, sweep kernels, D2H [Ψ; acc]} per (accumulator
+  // parity, counter-set parity): captured the second time the same pinned host buffers are
+  // passed with unchanged options; any option / reserve / comm change invalidates (version)
+  struct SweepGraph {
+    cudaGraphExec_t exec = nullptr;
+    const double* v = nullptr;
+    double* psi = nullptr;
+    unsigned long long version = 0;
+    const double* seen_v = nullptr;  // key of the last eager call (capture on the next match)
+    double* seen_psi = nullptr;
+    unsigned long long seen_version = ~0ull;
+    int64_t launches = 0;            // kernel launches one replay stands for
+    int tma_delta = 0;               // TMA sweeps one replay stands for
+  } graphs[2][2];
+  unsigned long long state_version = 1;
+  int use_graphs = 1;
+  const void* pinned_ok[2] = {nullptr, nullptr};  // host pointers already verified as pinned
+  DevBuf<unsigned> d_steal;     // TMA kernel: per-CTA chunk counters, two sets (sweep parity)
+  int steal = 1;                // 1 = CTAs that drain their range take chunks from others
+  unsigned long long tma_sweeps = 0;
   // resident CTAs per SM of every kernel instantiation this context has launched.
   // Per context, not per process: cudaFuncSetAttribute (the > 48 KB dynamic shared
   // memory opt-in) acts on the current device only, and contexts of one process
@@ -177,7 +201,15 @@ int check_common(cfmm_ctx* ctx, int64_t m, const double* R, const double* gamma,
   if (m < 0) return fail(ctx, CFMM_ERR_INVALID, "negative pool count");
   if (m > 0 && (!gamma || !Ai || !R))
     return fail(ctx, CFMM_ERR_INVALID, "null array argument");
+  // first offending pool, if any (parallel scan; the error names the lowest index like a serial one)
+  int64_t bad = m;
+  const int64_t nt = ctx->n_tokens;
+#pragma omp parallel for schedule(static) reduction(min : bad) if (m > (1 << 16))
   for (int64_t i = 0; i < m; ++i) {
+    const int64_t a = Ai[2 * i], b = Ai[2 * i + 1];
+    if (a < 1 || a > nt || b < 1 || b > nt || a == b) bad = i < bad ? i : bad;
+  }
+  for (int64_t i = bad; i < m && i == bad; ++i) {
     const int64_t a = Ai[2 * i], b = Ai[2 * i + 1];
     if (a < 1 || a > ctx->n_tokens || b < 1 || b > ctx->n_tokens)
       return fail(ctx, CFMM_ERR_INVALID,
@@ -198,7 +230,14 @@ void append_common(cfmm_ctx* ctx, PoolSet& s, int64_t m, const double* R,
   if (R) s.R.insert(s.R.end(), R, R + 2 * m);
   s.gamma.insert(s.gamma.end(), gamma, gamma + m);
   s.Ai.insert(s.Ai.end(), Ai, Ai + 2 * m);
-  for (int64_t i = 0; i < m; ++i) s.gidx.push_back(ctx->n_pools + i);
+  {
+    const size_t old = s.gidx.size();
+    s.gidx.resize(old + (size_t)m);
+    int64_t* gi = s.gidx.data() + old;
+    const int64_t base = ctx->n_pools;
+#pragma omp parallel for schedule(static) if (m > (1 << 16))
+    for (int64_t i = 0; i < m; ++i) gi[i] = base + i;
+  }
   s.m += m;
   ctx->n_pools += m;
 }
@@ -217,7 +256,7 @@ cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, in
   return cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree, product, shape, shape);
 }
 
-int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s);
+int refresh_scale(cfmm_ctx* ctx, PoolSet& s);
 
 int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
@@ -231,45 +270,62 @@ int upload_set(cfmm_ctx* ctx, int type) {
   s.m_padded = lay.m_padded;
   s.tma_ok = lay.bucketed;
   s.nb = (int)lay.nb;
-  s.chunk_bucket = lay.tile_bucket;
-  s.sched_grid = 0;
+  if (s.tma_ok) {
+    // bucket boundaries in chunks, for the kernel-parameter table
+    const int B = lay.tile_bucket.empty() ? 0 : lay.tile_bucket.back() + 1;
+    if (B > cfmm::kTmaMaxBuckets) {
+      s.tma_ok = false;  // more b-buckets than the parameter table holds: first-generation kernel
+    } else {
+      s.n_chunks = (int64_t)lay.tile_bucket.size();
+      s.buckets.n_buckets = B;
+      int b = 0;
+      s.buckets.first_chunk[0] = 0;
+      for (int64_t c = 0; c < s.n_chunks; ++c)
+        while (b < lay.tile_bucket[(size_t)c]) s.buckets.first_chunk[++b] = (int)c;
+      while (b < B) s.buckets.first_chunk[++b] = (int)s.n_chunks;
+    }
+  }
   const int64_t mp = s.m_padded;
   std::vector<double> gam((size_t)mp, 1.0);
   std::vector<int2> ai((size_t)mp);
   std::vector<int64_t> gidx((size_t)mp, -1);
-  int2 last = make_int2(0, 1);
+#pragma omp parallel for schedule(static) if (mp > (1 << 16))
   for (int64_t p = 0; p < mp; ++p) {
     const int64_t i = s.order[(size_t)p];
-    if (i < 0) {
-      // padding: keyed like the previous real pool of the bucket (monotone a);
-      // a leading pad of an empty-fronted bucket cannot occur (pads trail)
-      ai[(size_t)p] = last;
-      continue;
-    }
+    if (i < 0) continue;
     gam[(size_t)p] = s.gamma[(size_t)i];
-    last = make_int2(oa[(size_t)i], ob[(size_t)i]);
-    ai[(size_t)p] = last;
+    ai[(size_t)p] = make_int2(oa[(size_t)i], ob[(size_t)i]);
     // bit 62 of the global index marks a pool stored with its tokens exchanged
     gidx[(size_t)p] = s.gidx[(size_t)i] | (s.swapped[(size_t)i] ? (1ll << 62) : 0);
+  }
+  {
+    // padding: keyed like the previous real pool of the bucket (monotone a); pads trail
+    // their bucket, so a serial pass that only touches pads fixes them up
+    int2 last = make_int2(0, 1);
+    for (int64_t p = 0; p < mp; ++p) {
+      if (s.order[(size_t)p] < 0) ai[(size_t)p] = last; else last = ai[(size_t)p];
+    }
   }
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
   CU_TRY(ctx, s.d_gidx.upload(gidx));
   if (type != CFMM_POOL_UNIV3) {
     std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
-    bool ok = true;
+    int bad_range = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad_range) if (mp > (1 << 16))
     for (int64_t p = 0; p < mp; ++p) {
       const int64_t i = s.order[(size_t)p];
       if (i < 0) continue;
       r[(size_t)p] = s.swapped[(size_t)i] ? make_double2(s.R[2 * i + 1], s.R[2 * i])
                                           : make_double2(s.R[2 * i], s.R[2 * i + 1]);
-      ok = ok && fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
-           fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
+      const bool ok = fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
+                      fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
+      bad_range |= ok ? 0 : 1;
     }
-    s.in_fast_range = ok;
+    s.in_fast_range = bad_range == 0;
     CU_TRY(ctx, s.d_R.upload(r));
     if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
-      int rc = refresh_scaled_reserves(ctx, s);
+      int rc = refresh_scale(ctx, s);
       if (rc != CFMM_OK) return rc;
     }
   }
@@ -403,23 +459,18 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
   return CFMM_OK;
 }
 
-// (Re)build the derived scaled-reserve copy and the per-token scale table of the
-// fixed-point slice (three small kernels, off the hot path: finalize and every
-// reserve mutation).  fixed_ok tells the launcher whether the pool set qualifies.
-int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s) {
+// (Re)compute the per-token scale table of the fixed-point slice and whether the pool set
+// qualifies for it (three small kernels, off the hot path: finalize and every reserve
+// mutation).  Marks the packed stream stale.
+int refresh_scale(cfmm_ctx* ctx, PoolSet& s) {
   s.fixed_ok = false;
+  s.packed_mode = -1;
   if (!s.tma_ok || s.m_padded == 0) return CFMM_OK;
   const int64_t mp = s.m_padded;
   const int n = (int)ctx->n_tokens;
   cudaStream_t st = ctx->stream;
   const int threads = 256;
   const unsigned pblocks = (unsigned)((mp + threads - 1) / threads);
-  if (s.d_ig.n != (size_t)mp) {  // γ never changes after finalize
-    CU_TRY(ctx, s.d_ig.alloc((size_t)mp));
-    cfmm::inv_gamma_kernel<<<pblocks, threads, 0, st>>>(s.d_gam.p, mp, s.d_ig.p);
-    ctx->launches++;
-  }
-  if (s.d_Rs.n != (size_t)mp) CU_TRY(ctx, s.d_Rs.alloc((size_t)mp));
   if (s.d_inv_scale.n != (size_t)n) CU_TRY(ctx, s.d_inv_scale.alloc((size_t)n));
   if (s.d_tok_sum.n != (size_t)n + 2) CU_TRY(ctx, s.d_tok_sum.alloc((size_t)n + 2));  // + 2 flag words
   CU_TRY(ctx, cudaMemsetAsync(s.d_tok_sum.p, 0, ((size_t)n + 2) * sizeof(double), st));
@@ -427,10 +478,10 @@ int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s) {
   cfmm::token_reserve_sum_kernel<<<pblocks, threads, 0, st>>>(s.d_R.p, s.d_Ai.p, mp, s.d_tok_sum.p);
   cfmm::token_scale_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
       s.d_tok_sum.p, n, s.d_inv_scale.p, d_flags);
-  cfmm::scaled_reserves_kernel<<<pblocks, threads, 0, st>>>(s.d_R.p, s.d_Ai.p, mp, s.d_tok_sum.p,
-                                                          s.d_inv_scale.p, s.d_Rs.p, d_flags);
+  cfmm::scale_check_kernel<<<pblocks, threads, 0, st>>>(s.d_R.p, s.d_Ai.p, mp, s.d_tok_sum.p,
+                                                      s.d_inv_scale.p, d_flags);
   ctx->launches += 3;
-  int h_flags[4] = {0, 0, 0, 0};
+  int h_flags[2] = {0, 0};
   CU_TRY(ctx, cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   CU_TRY(ctx, cudaGetLastError());
@@ -438,16 +489,18 @@ int refresh_scaled_reserves(cfmm_ctx* ctx, PoolSet& s) {
   return CFMM_OK;
 }
 
-// upload the tile schedule for `grid` CTAs (rebuilt only when the grid or tile size changes)
-int ensure_schedule(cfmm_ctx* ctx, PoolSet& s, int grid) {
-  if (s.sched_grid == grid && s.sched_max_chunks == ctx->tile_chunks) return CFMM_OK;
-  const cfmm::TileSchedule ts = cfmm::build_tile_schedule(s.chunk_bucket, grid, ctx->tile_chunks);
-  static_assert(sizeof(int4) == 4 * sizeof(int), "tile descriptor packing");
-  CU_TRY(ctx, s.d_tile_desc.alloc(ts.desc.size() / 4));
-  CU_TRY(ctx, cudaMemcpy(s.d_tile_desc.p, ts.desc.data(), ts.desc.size() * sizeof(int), cudaMemcpyHostToDevice));
-  CU_TRY(ctx, s.d_cta_tile_start.upload(ts.cta_start));
-  s.sched_grid = grid;
-  s.sched_max_chunks = ctx->tile_chunks;
+// the packed stream of the mode this sweep runs in (rebuilt when the mode or the reserves changed)
+int ensure_packed(cfmm_ctx* ctx, PoolSet& s, bool econ, bool fixed, cudaStream_t st) {
+  const int mode = (econ ? 1 : 0) | (fixed ? 2 : 0);
+  if (s.packed_mode == mode) return CFMM_OK;
+  const size_t bytes = (size_t)s.n_chunks * cfmm::kTmaChunkBytes;
+  if (s.d_packed.n != bytes) CU_TRY(ctx, s.d_packed.alloc(bytes));
+  const int threads = 256;
+  cfmm::pack_chunks_kernel<<<(unsigned)((s.m_padded + threads - 1) / threads), threads, 0, st>>>(
+      s.d_R.p, s.d_gam.p, s.d_Ai.p, s.m_padded, fixed ? s.d_inv_scale.p : nullptr, econ ? 1 : 0, s.d_packed.p);
+  ctx->launches++;
+  CU_TRY(ctx, cudaGetLastError());
+  s.packed_mode = mode;
   return CFMM_OK;
 }
 
@@ -463,12 +516,24 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
                                                               cfmm::kTmaSmemBytes));
     if (occ < 1) return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma does not fit on an SM");
   }
-  const int64_t n_chunks = (int64_t)s.chunk_bucket.size();
+  int rc = ensure_packed(ctx, s, ECON, FIXED, st);
+  if (rc != CFMM_OK) return rc;
+  constexpr int kStealCtas = 2048;                             // CTAs per counter set
+  constexpr int kStealCap = kStealCtas * cfmm::kStealStride;  // words per set
+  if (!ctx->d_steal.n) {
+    CU_TRY(ctx, ctx->d_steal.alloc(2 * kStealCap));
+    std::vector<unsigned> init(2 * kStealCap, (unsigned)(cfmm::kTmaPrimed * cfmm::kTmaWarps));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_steal.p, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
-  if (grid > n_chunks) grid = (int)n_chunks;
-  int rc = ensure_schedule(ctx, s, grid);
-  if (rc != CFMM_OK) return rc;
+  if (grid > s.n_chunks) grid = (int)s.n_chunks;
+  if (grid > kStealCtas) grid = kStealCtas;
+  cfmm::StealCtl sc;
+  sc.cnt = ctx->d_steal.p + (ctx->tma_sweeps & 1) * kStealCap;
+  sc.cnt_next = ctx->d_steal.p + ((ctx->tma_sweeps + 1) & 1) * kStealCap;
+  sc.enabled = ctx->steal;
+  ctx->tma_sweeps++;
   cfmm::FusedExchange fx = ctx->fx_pending;
   if (fx.mode != 0) {
     fx.target = ctx->grid_done_target + (unsigned long long)grid;
@@ -477,9 +542,10 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   }
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
   kern<<<grid, cfmm::kTmaThreads, cfmm::kTmaSmemBytes, st>>>(
-      FIXED ? s.d_Rs.p : s.d_R.p, s.d_gam.p, s.d_ig.p, s.d_Ai.p, s.d_tile_desc.p, s.d_cta_tile_start.p, s.nb, d_v,
-      FIXED ? s.d_inv_scale.p : nullptr, d_psi, (int)ctx->n_tokens, take_zero_pending(ctx),
-      s.in_fast_range ? 1 : 0, ctx->exact, fx);
+      s.d_packed.p, s.d_gam.p, s.buckets, s.nb, d_v, FIXED ? s.d_inv_scale.p : nullptr, d_psi,
+      (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0, ctx->exact, fx, sc,
+      ctx->d_trace.n ? ctx->d_trace.p : nullptr);
+  if (ctx->d_trace.n) ctx->trace_grid = grid;
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   // the grid-barrier target moves only once the launch is known to be accepted
@@ -513,6 +579,7 @@ int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_p
 int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
                   cudaStream_t st, const double** view) {
   if (ctx->sweep_events) CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+  ctx->events_recorded = ctx->sweep_events != 0;
   ctx->epoch++;
   double* d_psi = ctx->d_accum[ctx->epoch & 1].p;
   ctx->zero_pending = ctx->d_accum[(ctx->epoch + 1) & 1].p;
@@ -522,7 +589,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
   bool fused = false;
   {
     const PoolSet& ps = ctx->sets[CFMM_POOL_PRODUCT];
-    if (ctx->comm.attached() && ctx->fused_exchange && !mat && ps.m > 0 && ps.tma_ok && ctx->use_tma &&
+    if (ctx->comm.attached() && !ctx->exchange_bypass && ctx->fused_exchange && !mat && ps.m > 0 && ps.tma_ok && ctx->use_tma &&
         ctx->debug_skip == 0 && ctx->sets[CFMM_POOL_GEOMEAN].m == 0 && ctx->sets[CFMM_POOL_UNIV3].m == 0) {
       fused = true;
       ctx->fx_pending.view = ctx->comm.view();
@@ -572,7 +639,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
   const double* result = d_psi;
   if (fused) {
     result = d_dst ? d_dst : d_psi;
-  } else if (ctx->comm.attached()) {
+  } else if (ctx->comm.attached() && !ctx->exchange_bypass) {
     ProfScope prof(ctx, 3, st);
     double* dst = d_dst ? d_dst : d_psi;
     if (!ctx->comm.all_reduce(d_psi, dst, ctx->n_tokens + 1, st))
@@ -658,16 +725,23 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   return CFMM_OK;
 }
 
+namespace {
+void drop_graphs(cfmm_ctx* ctx);
+}
+
 void cfmm_destroy(cfmm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->comm.detach();
+  drop_graphs(ctx);
   for (auto e : ctx->prof.ev)
     if (e) cudaEventDestroy(e);
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_grid_done.release();
+  ctx->d_steal.release();
+  ctx->d_trace.release();
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -737,6 +811,93 @@ int cfmm_add_univ3(cfmm_ctx* ctx, int64_t m, const double* current_price,
   return CFMM_OK;
 }
 
+// ---- flat pool files (an ingest format that is not an array of heap
+// objects).  Little-endian, 64-byte header {magic "CFMMPOOL", u32 version = 1, u32 pool
+// type, i64 m, i64 n_tokens, zero pad}, then the SoA arrays exactly as cfmm_add_* take
+// them: R [2m] f64, gamma [m] f64, Ai [2m] i64 (1-based), and w [2m] f64 for
+// GeometricMeanTwoCoin.  The file is mmap-ed; cfmm_add_pool_file feeds it to cfmm_add_*.
+namespace {
+struct PoolFileHeader {
+  char magic[8];
+  uint32_t version, type;
+  int64_t m, n_tokens;
+  char pad[32];
+};
+static_assert(sizeof(PoolFileHeader) == 64, "pool file header");
+
+size_t pool_file_bytes(int type, int64_t m) {
+  return sizeof(PoolFileHeader) + (size_t)m * (16 + 8 + 16 + (type == CFMM_POOL_GEOMEAN ? 16 : 0));
+}
+}  // namespace
+
+int cfmm_pool_file_write(const char* path, int type, int64_t n_tokens, int64_t m, const double* R,
+                         const double* gamma, const int64_t* Ai, const double* w) {
+  if (!path || m < 0 || n_tokens < 1 || (type != CFMM_POOL_PRODUCT && type != CFMM_POOL_GEOMEAN) ||
+      (m > 0 && (!R || !gamma || !Ai || (type == CFMM_POOL_GEOMEAN && !w))))
+    return CFMM_ERR_INVALID;
+  FILE* f = fopen(path, "wb");
+  if (!f) return CFMM_ERR_INVALID;
+  PoolFileHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "CFMMPOOL", 8);
+  h.version = 1;
+  h.type = (uint32_t)type;
+  h.m = m;
+  h.n_tokens = n_tokens;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  ok = ok && fwrite(R, 16, (size_t)m, f) == (size_t)m && fwrite(gamma, 8, (size_t)m, f) == (size_t)m &&
+       fwrite(Ai, 16, (size_t)m, f) == (size_t)m;
+  if (type == CFMM_POOL_GEOMEAN) ok = ok && fwrite(w, 16, (size_t)m, f) == (size_t)m;
+  ok = (fclose(f) == 0) && ok;
+  return ok ? CFMM_OK : CFMM_ERR_INVALID;
+}
+
+int cfmm_pool_file_info(const char* path, int* type, int64_t* n_tokens, int64_t* m) {
+  if (!path || !type || !n_tokens || !m) return CFMM_ERR_INVALID;
+  FILE* f = fopen(path, "rb");
+  if (!f) return CFMM_ERR_INVALID;
+  PoolFileHeader h;
+  const bool ok = fread(&h, sizeof(h), 1, f) == 1;
+  fseek(f, 0, SEEK_END);
+  const long size = ftell(f);
+  fclose(f);
+  if (!ok || memcmp(h.magic, "CFMMPOOL", 8) != 0 || h.version != 1 || h.m < 0 ||
+      (h.type != CFMM_POOL_PRODUCT && h.type != CFMM_POOL_GEOMEAN) ||
+      (size_t)size != pool_file_bytes((int)h.type, h.m))
+    return CFMM_ERR_INVALID;
+  *type = (int)h.type;
+  *n_tokens = h.n_tokens;
+  *m = h.m;
+  return CFMM_OK;
+}
+
+int cfmm_add_pool_file(cfmm_ctx* ctx, const char* path) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  int type = 0;
+  int64_t n_tokens = 0, m = 0;
+  if (cfmm_pool_file_info(path, &type, &n_tokens, &m) != CFMM_OK)
+    return fail(ctx, CFMM_ERR_INVALID, "'%s' is not a readable CFMM pool file", path ? path : "(null)");
+  if (n_tokens != ctx->n_tokens)
+    return fail(ctx, CFMM_ERR_INVALID, "pool file is for %lld tokens, the context for %lld",
+                (long long)n_tokens, (long long)ctx->n_tokens);
+  if (m == 0) return CFMM_OK;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(ctx, CFMM_ERR_INVALID, "cannot open '%s'", path);
+  const size_t bytes = pool_file_bytes(type, m);
+  void* map = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return fail(ctx, CFMM_ERR_NOMEM, "mmap of '%s' failed", path);
+  const char* base = (const char*)map + sizeof(PoolFileHeader);
+  const double* R = (const double*)base;
+  const double* gamma = R + 2 * m;
+  const int64_t* Ai = (const int64_t*)(gamma + m);
+  const double* w = (const double*)(Ai + 2 * m);
+  const int rc = type == CFMM_POOL_PRODUCT ? cfmm_add_product(ctx, m, R, gamma, Ai)
+                                           : cfmm_add_geomean(ctx, m, R, gamma, Ai, w);
+  munmap(map, bytes);
+  return rc;
+}
+
 int cfmm_finalize(cfmm_ctx* ctx) {
   if (!ctx) return CFMM_ERR_INVALID;
   if (ctx->finalized) return fail(ctx, CFMM_ERR_STATE, "already finalized");
@@ -773,6 +934,31 @@ int cfmm_sweep_device_view(cfmm_ctx* ctx, const double* d_v, int materialize, vo
   return enqueue_sweep(ctx, d_v, nullptr, materialize != 0, st, d_psi_acc_out);
 }
 
+namespace {
+
+bool host_pinned(cfmm_ctx* ctx, const void* p) {
+  if (p == ctx->pinned_ok[0] || p == ctx->pinned_ok[1]) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type != cudaMemoryTypeHost) return false;
+  ctx->pinned_ok[1] = ctx->pinned_ok[0];
+  ctx->pinned_ok[0] = p;
+  return true;
+}
+
+void drop_graphs(cfmm_ctx* ctx) {
+  for (auto& row : ctx->graphs)
+    for (auto& g : row) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g = cfmm_ctx::SweepGraph();
+    }
+}
+
+}  // namespace
+
 int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
                int materialize) {
   int rc = ready(ctx);
@@ -782,11 +968,72 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t nb = (size_t)ctx->n_tokens * sizeof(double);
   cudaStream_t st = ctx->stream;
+  const bool contiguous = acc_out == psi_out + ctx->n_tokens;
+
+  // ---- graph path: the whole call is one cudaGraphLaunch ---------------------------------
+  const bool graphable = ctx->use_graphs && !materialize && contiguous && !ctx->sweep_events &&
+                         !ctx->comm.attached() && ctx->prof.type.empty() && !ctx->d_trace.n &&
+                         ctx->debug_skip == 0;
+  cfmm_ctx::SweepGraph* g = nullptr;
+  if (graphable) {
+    g = &ctx->graphs[(ctx->epoch + 1) & 1][ctx->tma_sweeps & 1];
+    if (g->exec && g->v == v && g->psi == psi_out && g->version == ctx->state_version) {
+      ctx->epoch++;
+      ctx->tma_sweeps += (unsigned long long)g->tma_delta;
+      ctx->launches += g->launches;
+      ctx->events_recorded = false;
+      CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
+      CU_TRY(ctx, cudaStreamSynchronize(st));
+      return CFMM_OK;
+    }
+    const bool second = g->seen_v == v && g->seen_psi == psi_out && g->seen_version == ctx->state_version;
+    if (second && host_pinned(ctx, v) && host_pinned(ctx, psi_out)) {
+      // same buffers, same options as the last call on this parity: capture
+      if (g->exec) cudaGraphExecDestroy(g->exec);
+      g->exec = nullptr;
+      const int64_t l0 = ctx->launches;
+      const unsigned long long t0 = ctx->tma_sweeps;
+      cudaGraph_t graph = nullptr;
+      CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      cudaError_t e = cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st);
+      const double* res = nullptr;
+      if (e == cudaSuccess) rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, false, st, &res);
+      if (e == cudaSuccess && rc == CFMM_OK)
+        e = cudaMemcpyAsync(psi_out, res, nb + sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+      if (e == cudaSuccess && rc == CFMM_OK && e2 == cudaSuccess && graph &&
+          cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+        g->v = v;
+        g->psi = psi_out;
+        g->version = ctx->state_version;
+        g->launches = ctx->launches - l0;
+        g->tma_delta = (int)(ctx->tma_sweeps - t0);
+        cudaGraphDestroy(graph);
+        CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        return CFMM_OK;
+      }
+      // capture failed: the sweep state has advanced without any work being done -- undo and
+      // take the eager path for good
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g->exec = nullptr;
+      ctx->use_graphs = 0;
+      ctx->epoch--;
+      ctx->tma_sweeps = t0;
+      ctx->launches = l0;
+      if (rc != CFMM_OK) return rc;
+    }
+    g->seen_v = v;
+    g->seen_psi = psi_out;
+    g->seen_version = ctx->state_version;
+  }
+
   CU_TRY(ctx, cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st));
   const double* res = nullptr;
   rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, materialize != 0, st, &res);
   if (rc != CFMM_OK) return rc;
-  if (acc_out == psi_out + ctx->n_tokens) {
+  if (contiguous) {
     // caller keeps [psi ; acc] contiguous: one D2H copy
     CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb + sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -804,6 +1051,8 @@ int cfmm_last_sweep_ms(cfmm_ctx* ctx, float* ms_out) {
   int rc = ready(ctx);
   if (rc != CFMM_OK) return rc;
   if (!ms_out) return fail(ctx, CFMM_ERR_INVALID, "ms_out is NULL");
+  if (!ctx->events_recorded)
+    return fail(ctx, CFMM_ERR_STATE, "the last sweep recorded no events: set option \"sweep_events\" to 1 first");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
   CU_TRY(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
@@ -853,6 +1102,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   if (type != CFMM_POOL_PRODUCT && type != CFMM_POOL_GEOMEAN)
     return fail(ctx, CFMM_ERR_INVALID, "update_reserves: type must be PRODUCT or GEOMEAN");
   PoolSet& s = ctx->sets[type];
+  ctx->state_version++;
   if (first < 0 || count < 0 || first + count > s.m)
     return fail(ctx, CFMM_ERR_INVALID, "update_reserves: range [%lld, %lld) outside 0..%lld",
                 (long long)first, (long long)(first + count), (long long)s.m);
@@ -888,7 +1138,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   d_pos.release();
   if (e != cudaSuccess)
     return fail(ctx, CFMM_ERR_CUDA, "update_reserves failed: %s", cudaGetErrorString(e));
-  if (type == CFMM_POOL_PRODUCT) return refresh_scaled_reserves(ctx, s);
+  if (type == CFMM_POOL_PRODUCT) return refresh_scale(ctx, s);
   return CFMM_OK;
 }
 
@@ -903,6 +1153,7 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
                 "cfmm_apply_trades: UniV3 pools have no explicit reserves (R + γΔ − Λ is defined for "
                 "ProductTwoCoin / GeometricMeanTwoCoin only)");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->state_version++;
   DevBuf<int> flag;
   std::vector<int> zero(1, 0);
   for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) {
@@ -922,7 +1173,7 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
     if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "apply_trades failed: %s", cudaGetErrorString(e));
     if (h) s.in_fast_range = false;  // later sweeps take the generic (guarded) form
     if (t == CFMM_POOL_PRODUCT) {
-      int rc2 = refresh_scaled_reserves(ctx, s);
+      int rc2 = refresh_scale(ctx, s);
       if (rc2 != CFMM_OK) return rc2;
     }
   }
@@ -931,6 +1182,11 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
 
 int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return CFMM_ERR_INVALID;
+  ctx->state_version++;  // captured sweep graphs are stale
+  if (!strcmp(key, "sweep_graphs")) {
+    ctx->use_graphs = value != 0;
+    return CFMM_OK;
+  }
   if (!strcmp(key, "exact")) {
     ctx->exact = value != 0;
   } else if (!strcmp(key, "blocks_per_sm")) {
@@ -947,11 +1203,22 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->orient_by_degree = value < 0 ? -1 : (value != 0);
   } else if (!strcmp(key, "psi_fixed_point")) {
     ctx->psi_fixed_point = value != 0;
-  } else if (!strcmp(key, "tile_chunks")) {
-    if (value < 1 || value > cfmm::kTmaWarps) return fail(ctx, CFMM_ERR_INVALID, "tile_chunks out of range 1..14");
-    ctx->tile_chunks = (int)value;
+  } else if (!strcmp(key, "steal")) {
+    ctx->steal = value != 0;
+  } else if (!strcmp(key, "trace")) {
+    // measurement only: 1 = every TMA sweep records per-CTA phase timestamps (cfmm_debug_read_trace)
+    cudaSetDevice(ctx->device);
+    if (value) {
+      CU_TRY(ctx, ctx->d_trace.alloc((size_t)8 * 4096));
+      CU_TRY(ctx, cudaMemset(ctx->d_trace.p, 0, 8 * 4096 * sizeof(unsigned long long)));
+    } else {
+      cudaStreamSynchronize(ctx->stream);
+      ctx->d_trace.release();
+    }
   } else if (!strcmp(key, "fused_exchange")) {
     ctx->fused_exchange = value != 0;
+  } else if (!strcmp(key, "exchange_bypass")) {
+    ctx->exchange_bypass = value != 0;
   } else if (!strcmp(key, "exchange_two_shot")) {
     ctx->comm.force_mode((int)value);
   } else if (!strcmp(key, "sweep_events")) {
@@ -1060,20 +1327,18 @@ int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t* Ai, in
   return CFMM_OK;
 }
 
-// Test hook (no CUDA call): the tile schedule of the TMA kernel for a chunk->bucket map.
-// desc_out [4 * cap_tiles] and cta_start_out [grid + 1] are filled when they are large enough;
-// counts_out[2] = {tiles, grid used}.
-int cfmm_debug_tile_schedule(const int32_t* chunk_bucket, int64_t n_chunks, int grid, int max_chunks,
-                             int64_t cap_tiles, int32_t* desc_out, int32_t* cta_start_out,
-                             int64_t* counts_out) {
-  if (!chunk_bucket || !counts_out || n_chunks < 1 || grid < 1 || max_chunks < 1) return CFMM_ERR_INVALID;
-  const std::vector<int> cb(chunk_bucket, chunk_bucket + n_chunks);
-  const cfmm::TileSchedule ts = cfmm::build_tile_schedule(cb, grid, max_chunks);
-  counts_out[0] = (int64_t)(ts.desc.size() / 4);
-  counts_out[1] = ts.grid;
-  if (desc_out && cta_start_out && cap_tiles >= counts_out[0]) {
-    memcpy(desc_out, ts.desc.data(), ts.desc.size() * sizeof(int));
-    memcpy(cta_start_out, ts.cta_start.data(), ts.cta_start.size() * sizeof(int));
+// Measurement hook: the per-CTA phase timestamps (ns, %globaltimer) of the last TMA sweep
+// recorded under option "trace": out[8 * grid] = per CTA {entry, slice ready, chunk loop
+// done, partials flushed, grid barrier passed (fused exchange), exit, SM id, 0}.
+int cfmm_debug_read_trace(cfmm_ctx* ctx, uint64_t* out, int64_t cap_ctas, int64_t* grid_out) {
+  if (!ctx || !grid_out) return CFMM_ERR_INVALID;
+  if (!ctx->d_trace.n) return fail(ctx, CFMM_ERR_STATE, "option \"trace\" is off");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  *grid_out = ctx->trace_grid;
+  if (out && cap_ctas >= ctx->trace_grid && ctx->trace_grid > 0) {
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    CU_TRY(ctx, cudaMemcpy(out, ctx->d_trace.p, (size_t)ctx->trace_grid * 8 * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost));
   }
   return CFMM_OK;
 }
@@ -1125,6 +1390,7 @@ int cfmm_comm_attach(cfmm_ctx* ctx, int world, int rank, const void* handles) {
   if (world < 1 || world > cfmm::kMaxPeers || rank < 0 || rank >= world)
     return fail(ctx, CFMM_ERR_INVALID, "bad world/rank %d/%d", rank, world);
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  ctx->state_version++;
   if (!ctx->comm.attach(world, rank, (const unsigned char*)handles,
                         CFMM_COMM_HANDLE_BYTES, ctx->sm_count))
     return fail(ctx, CFMM_ERR_COMM, "comm attach failed: %s", ctx->comm.error().c_str());

@@ -10,8 +10,56 @@
 #pragma once
 #include <cstdint>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace cfmm {
+
+// Stable counting sort of the items 0..m-1 by key(item) in [0, K), over `src` (the current
+// order; null = identity): out[pos] = item.  Parallel form: every thread counts and then
+// scatters its own contiguous block, with per-(key, thread) offsets -- stable, no atomics.
+template <class KeyFn>
+inline void counting_sort_stable(const int64_t* src, int64_t m, int64_t K, KeyFn key,
+                                 std::vector<int64_t>& out) {
+  out.assign((size_t)m, 0);
+  int T = 1;
+#ifdef _OPENMP
+  T = omp_get_max_threads();
+  const int64_t cap = (int64_t)32 << 20;  // counters in flight
+  if ((int64_t)T * K > cap) T = (int)(cap / (K > 0 ? K : 1));
+  if (T < 1) T = 1;
+  if (m < (1 << 16)) T = 1;
+#endif
+  std::vector<int64_t> cnt((size_t)T * (size_t)K, 0);
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    const int64_t lo = m * t / T, hi = m * (t + 1) / T;
+    int64_t* c = cnt.data() + (size_t)t * (size_t)K;
+    for (int64_t p = lo; p < hi; ++p) c[key(src ? src[p] : p)]++;
+#pragma omp barrier
+#pragma omp single
+    {
+      int64_t run = 0;  // offsets in (key, thread) order
+      for (int64_t k = 0; k < K; ++k)
+        for (int tt = 0; tt < T; ++tt) {
+          int64_t& x = cnt[(size_t)tt * (size_t)K + (size_t)k];
+          const int64_t v = x;
+          x = run;
+          run += v;
+        }
+    }
+    for (int64_t p = lo; p < hi; ++p) {
+      const int64_t item = src ? src[p] : p;
+      out[(size_t)c[key(item)]++] = item;
+    }
+  }
+}
 
 struct TileShape {
   int64_t tile = 0;   // padding unit in pools (one warp-chunk of the TMA kernel); 0 = no bucketing
@@ -44,8 +92,11 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
   std::vector<int64_t> deg;
   if (symmetric && orient != 0) {
     deg.assign((size_t)n_tokens, 0);
+#pragma omp parallel for schedule(static) if (m > (1 << 16))
     for (int64_t i = 0; i < m; ++i) {
+#pragma omp atomic
       deg[(size_t)Ai[2 * i] - 1]++;
+#pragma omp atomic
       deg[(size_t)Ai[2 * i + 1] - 1]++;
     }
     // hub detection: some token sits in far more pools than the average token.
@@ -57,6 +108,7 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     lay.skewed = (double)max_deg > 4.0 * mean_deg + 64.0;
     if (orient < 0 && !lay.skewed) deg.clear();
   }
+#pragma omp parallel for schedule(static) if (m > (1 << 16))
   for (int64_t i = 0; i < m; ++i) {
     const int a = (int)(Ai[2 * i] - 1), b = (int)(Ai[2 * i + 1] - 1);
     const bool sw = !deg.empty() && deg[(size_t)b] > deg[(size_t)a];
@@ -65,13 +117,7 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     lay.ob[(size_t)i] = sw ? a : b;
   }
   // stable counting sort by the first token
-  {
-    std::vector<int64_t> head((size_t)n_tokens + 1, 0);
-    for (int64_t i = 0; i < m; ++i) head[(size_t)lay.oa[(size_t)i] + 1]++;
-    for (int64_t t = 0; t < n_tokens; ++t) head[(size_t)t + 1] += head[(size_t)t];
-    lay.order.assign((size_t)m, 0);
-    for (int64_t i = 0; i < m; ++i) lay.order[(size_t)head[(size_t)lay.oa[(size_t)i]]++] = i;
-  }
+  counting_sort_stable(nullptr, m, n_tokens, [&](int64_t i) { return (int64_t)lay.oa[(size_t)i]; }, lay.order);
   lay.used_skew_shape = lay.skewed && skew.tile > 0;
   const TileShape shape = lay.used_skew_shape ? skew : normal;
   if (shape.tile <= 0 || m == 0) return lay;
@@ -84,17 +130,36 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     if (up <= shape.nbmax) nb = up;
   }
   std::vector<int64_t> cnt((size_t)B + 1, 0);
-  for (int64_t i = 0; i < m; ++i) cnt[(size_t)(lay.ob[(size_t)i] / nb) + 1]++;
+  std::vector<int64_t> grouped;  // the a-sorted order, stably regrouped by bucket(b)
+  counting_sort_stable(lay.order.data(), m, B, [&](int64_t i) { return (int64_t)(lay.ob[(size_t)i] / nb); },
+                       grouped);
+  {
+    // bucket sizes from the grouped order: bucket ids are non-decreasing along it
+    std::vector<int64_t> c2((size_t)B, 0);
+#pragma omp parallel for schedule(static) if (m > (1 << 16))
+    for (int64_t i = 0; i < m; ++i) {
+#pragma omp atomic
+      c2[(size_t)(lay.ob[(size_t)i] / nb)]++;
+    }
+    for (int64_t k = 0; k < B; ++k) cnt[(size_t)k + 1] = c2[(size_t)k];
+  }
   int64_t padded = 0;
   for (int64_t k = 0; k < B; ++k) padded += (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
   if (padded > 2 * m + 8 * tile) return lay;  // too sparse per bucket: a-sorted layout only
   std::vector<int64_t> start((size_t)B + 1, 0);  // padded start of each bucket
   for (int64_t k = 0; k < B; ++k)
     start[(size_t)k + 1] = start[(size_t)k] + (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
-  std::vector<int64_t> order((size_t)padded, -1), fill(start.begin(), start.end() - 1);
-  for (int64_t p = 0; p < m; ++p) {  // stable: keeps the a-order inside a bucket
-    const int64_t i = lay.order[(size_t)p];
-    order[(size_t)fill[(size_t)(lay.ob[(size_t)i] / nb)]++] = i;
+  std::vector<int64_t> order((size_t)padded, -1);
+  {
+    // grouped[] is the padded order minus the pads: bucket k's pools go to start[k] onwards
+    std::vector<int64_t> first((size_t)B + 1, 0);  // unpadded start of each bucket
+    for (int64_t k = 0; k < B; ++k) first[(size_t)k + 1] = first[(size_t)k] + cnt[(size_t)k + 1];
+#pragma omp parallel for schedule(static) if (m > (1 << 16))
+    for (int64_t q = 0; q < m; ++q) {
+      const int64_t i = grouped[(size_t)q];
+      const int64_t k = lay.ob[(size_t)i] / nb;
+      order[(size_t)(start[(size_t)k] + (q - first[(size_t)k]))] = i;
+    }
   }
   lay.order.swap(order);
   lay.m_padded = padded;
@@ -105,42 +170,6 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     for (int64_t t = start[(size_t)k] / tile; t < start[(size_t)k + 1] / tile; ++t)
       lay.tile_bucket[(size_t)t] = (int)k;
   return lay;
-}
-
-// ---- tile schedule of the TMA kernel ----------------------------------------------
-// The padded device order is a sequence of chunks (one warp's share of a tile);
-// chunk_bucket[c] is non-decreasing.  CTA g of `grid` owns the chunk range
-// [C*g/grid, C*(g+1)/grid) -- balanced to one chunk -- and walks it in tiles of up
-// to `max_chunks` consecutive chunks that never straddle a bucket boundary.
-struct TileSchedule {
-  std::vector<int> desc;       // 4 ints per tile: first chunk, chunk count, bucket, 0
-  std::vector<int> cta_start;  // [grid + 1] tile index ranges
-  int grid = 0;
-};
-
-inline TileSchedule build_tile_schedule(const std::vector<int>& chunk_bucket, int grid, int max_chunks) {
-  TileSchedule ts;
-  const int64_t C = (int64_t)chunk_bucket.size();
-  if (grid > C) grid = (int)C;
-  if (grid < 1) grid = 1;
-  ts.grid = grid;
-  ts.cta_start.assign((size_t)grid + 1, 0);
-  for (int g = 0; g < grid; ++g) {
-    const int64_t lo = C * g / grid, hi = C * (g + 1) / grid;
-    int64_t c = lo;
-    while (c < hi) {
-      const int bk = chunk_bucket[(size_t)c];
-      int64_t e = c + 1;
-      while (e < hi && e - c < max_chunks && chunk_bucket[(size_t)e] == bk) ++e;
-      ts.desc.push_back((int)c);
-      ts.desc.push_back((int)(e - c));
-      ts.desc.push_back(bk);
-      ts.desc.push_back(0);
-      c = e;
-    }
-    ts.cta_start[(size_t)g + 1] = (int)(ts.desc.size() / 4);
-  }
-  return ts;
 }
 
 }  // namespace cfmm

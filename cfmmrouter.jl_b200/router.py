@@ -16,7 +16,7 @@ from . import _lib
 from .cfmms import CFMM, GeometricMeanTwoCoin, ProductTwoCoin, UniV3
 from .objectives import Objective
 
-__all__ = ["DevicePools", "Router", "route", "find_arb", "netflows", "netflows_",
+__all__ = ["DevicePools", "write_pool_file", "pool_file_info", "Router", "route", "find_arb", "netflows", "netflows_",
            "update_reserves", "shard_range"]
 
 
@@ -35,6 +35,30 @@ def shard_range(m: int, world: int, rank: int):
     return lo, hi
 
 
+def write_pool_file(path, n_tokens: int, R, gamma, Ai, w=None):
+    """Write ProductTwoCoin (w is None) or GeometricMeanTwoCoin pools as a flat pool file."""
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 2)
+    gamma = np.ascontiguousarray(gamma, dtype=np.float64).reshape(-1)
+    Ai = np.ascontiguousarray(Ai, dtype=np.int64).reshape(-1, 2)
+    wp = None
+    if w is not None:
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 2)
+        wp = _dp(w)
+    rc = _lib.load().cfmm_pool_file_write(str(path).encode(), _lib.POOL_GEOMEAN if w is not None else _lib.POOL_PRODUCT,
+                                          int(n_tokens), len(gamma), _dp(R), _dp(gamma), _ip(Ai), wp)
+    if rc != _lib.CFMM_OK:
+        raise OSError(f"cannot write pool file {path}")
+
+
+def pool_file_info(path):
+    """(pool type, n_tokens, m) of a flat pool file."""
+    t, n, m = C.c_int(), C.c_int64(), C.c_int64()
+    rc = _lib.load().cfmm_pool_file_info(str(path).encode(), C.byref(t), C.byref(n), C.byref(m))
+    if rc != _lib.CFMM_OK:
+        raise OSError(f"{path} is not a CFMM pool file")
+    return t.value, n.value, m.value
+
+
 class DevicePools:
     """One GPU's shard of the pool set: a thin object wrapper over cfmm_ctx."""
 
@@ -50,6 +74,16 @@ class DevicePools:
         self.peer_attached = False
         self._psi = np.zeros(self.n_tokens)
         self._acc = C.c_double(0.0)
+        # pinned staging for sweep(): ν in, [Ψ; acc] out (contiguous) -- the buffers the library
+        # replays its {H2D, sweep, D2H} graph on (cfmm_b200.h, option "sweep_graphs")
+        nbytes = 8 * (2 * self.n_tokens + 1)
+        self._pin = self._lib.cfmm_host_alloc(nbytes)
+        if not self._pin:
+            self._lib.cfmm_destroy(self._ctx)
+            raise MemoryError("cfmm_host_alloc failed")
+        buf = (C.c_double * (2 * self.n_tokens + 1)).from_address(self._pin)
+        arr = np.frombuffer(buf, dtype=np.float64)
+        self._pin_nu, self._pin_out = arr[:self.n_tokens], arr[self.n_tokens:]
 
     # -- ingest -------------------------------------------------------------
     def _chk(self, rc):
@@ -85,6 +119,10 @@ class DevicePools:
         self._chk(self._lib.cfmm_add_univ3(self._ctx, len(cp), _dp(cp), _dp(gamma), _ip(Ai),
                                            _ip(off), _dp(lt), _dp(lq)))
 
+    def add_file(self, path: str):
+        """Add the pools of a flat pool file (write_pool_file / cfmm_pool_file_write)."""
+        self._chk(self._lib.cfmm_add_pool_file(self._ctx, str(path).encode()))
+
     def finalize(self):
         self._chk(self._lib.cfmm_finalize(self._ctx))
 
@@ -101,10 +139,13 @@ class DevicePools:
         v = np.ascontiguousarray(v, dtype=np.float64)
         if v.shape != (self.n_tokens,):
             raise ValueError(f"v must have length {self.n_tokens}")
-        psi = np.empty(self.n_tokens)
-        self._chk(self._lib.cfmm_sweep(self._ctx, _dp(v), _dp(psi), C.byref(self._acc),
-                                       1 if materialize else 0))
-        return psi, float(self._acc.value)
+        np.copyto(self._pin_nu, v)
+        base = self._pin
+        n8 = 8 * self.n_tokens
+        dp = C.POINTER(C.c_double)
+        self._chk(self._lib.cfmm_sweep(self._ctx, C.cast(base, dp), C.cast(base + n8, dp),
+                                       C.cast(base + 2 * n8, dp), 1 if materialize else 0))
+        return self._pin_out[:self.n_tokens].copy(), float(self._pin_out[self.n_tokens])
 
     def sweep_into(self, v_ptr: int, psi_ptr: int, acc_ptr: int, materialize: bool = False):
         """Raw-pointer form of sweep (host pointers, e.g. pinned buffers)."""
@@ -198,6 +239,10 @@ class DevicePools:
         if self._ctx:
             self._lib.cfmm_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            self._pin_nu = self._pin_out = None
+            if self._pin:
+                self._lib.cfmm_host_free(self._pin)
+                self._pin = None
 
     def __del__(self):
         try:

@@ -90,6 +90,17 @@ int cfmm_add_univ3(cfmm_ctx *ctx, int64_t m, const double *current_price,
                    const int64_t *tick_off, const double *lower_ticks,
                    const double *liquidity);
 
+/* Flat pool files: the ingest format for large pool sets (replaces building a
+ * Vector{CFMM} of heap objects, src/router.jl:18-35, src/cfmms.jl:101-111).  Little-endian,
+ * 64-byte header {"CFMMPOOL", u32 version 1, u32 cfmm_pool_type, i64 m, i64 n_tokens, pad},
+ * then R [2m] f64, gamma [m] f64, Ai [2m] i64 (1-based), and w [2m] f64 for
+ * GeometricMeanTwoCoin -- the arrays cfmm_add_product / cfmm_add_geomean take.
+ * cfmm_add_pool_file mmaps the file and adds its pools (same validation, same errors). */
+int cfmm_pool_file_write(const char *path, int type, int64_t n_tokens, int64_t m, const double *R,
+                         const double *gamma, const int64_t *Ai, const double *w /* geomean */);
+int cfmm_pool_file_info(const char *path, int *type, int64_t *n_tokens, int64_t *m);
+int cfmm_add_pool_file(cfmm_ctx *ctx, const char *path);
+
 /* Sort each pool type by its first token, lay it out SoA and upload. */
 int cfmm_finalize(cfmm_ctx *ctx);
 
@@ -166,15 +177,24 @@ int cfmm_apply_trades(cfmm_ctx *ctx);
  *                      -1 (default) = only when finalize detects hub tokens, 0 never,
  *                      1 always; before cfmm_finalize.
  *   "use_tma"          0 = run the first-generation kernel on the same layout.
- *   "blocks_per_sm" / "tile_chunks"   grid / tile-size measurement knobs.
+ *   "blocks_per_sm"    resident CTAs per SM of the persistent kernels (measurement knob).
  *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
  *                      in the sweep kernel's tail; 0 = separate exchange launch.
+ *   "exchange_bypass"  multi-GPU: 1 = sweeps skip the exchange and return this rank's partial
+ *                      [psi ; acc] (verification; every rank must set it alike).
  *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol
  *                      (default: two-shot for more than two ranks); after cfmm_comm_attach.
- *   "sweep_events"     0 = do not record the two CUDA events cfmm_last_sweep_ms needs.
+ *   "sweep_events"     1 = record the two CUDA events cfmm_last_sweep_ms needs around every
+ *                      sweep (default 0; turns the sweep graphs off).
+ *   "sweep_graphs"     1 (default) = cfmm_sweep replays {H2D nu, sweep, D2H [psi; acc]} as one
+ *                      CUDA graph once the same pinned host buffers (cfmm_host_alloc, psi and
+ *                      acc contiguous) have been passed twice with unchanged options.
  *   "geomean_log2"     gradient-only GeometricMean sweeps take the power as exp2(e*log2 t)
  *                      (1, default; <= 12 ulp over the admitted range, validated against
  *                      pow on hardware) or as pow (0).
+ *   "steal"            TMA kernel: 1 (default) = CTAs that finish their chunk range take chunks
+ *                      from the ranges of slower CTAs; 0 = static ranges only.
+ *   "trace"            1 = TMA sweeps record per-CTA phase timestamps (cfmm_debug_read_trace).
  *   "profile"          N = time the next N kernel launches (cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);
 
@@ -210,13 +230,10 @@ int cfmm_selftest_inrange_math(cfmm_ctx *ctx, const double *a, const double *b,
 int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t *Ai, int orient,
                               int variant, int64_t cap, int64_t *order_out,
                               int32_t *chunk_bucket_out, uint8_t *swapped_out, int64_t *info);
-/* Test hook, needs no device: the TMA kernel's tile schedule for a chunk -> bucket map
- * (non-decreasing) on `grid` CTAs with at most max_chunks chunks per tile.
- * counts_out[2] = {tiles, grid used}; desc_out [4 per tile: first chunk, chunk count,
- * bucket, 0] and cta_start_out [grid + 1] are filled when cap_tiles >= tiles. */
-int cfmm_debug_tile_schedule(const int32_t *chunk_bucket, int64_t n_chunks, int grid, int max_chunks,
-                             int64_t cap_tiles, int32_t *desc_out, int32_t *cta_start_out,
-                             int64_t *counts_out);
+/* Measurement hook (option "trace" = 1): per-CTA phase timestamps of the last TMA gradient
+ * sweep, ns of %globaltimer: out[8 * grid] = {entry, price slice ready, own range done,
+ * all chunks done, partials flushed, exit, SM id, chunks processed} per CTA. */
+int cfmm_debug_read_trace(cfmm_ctx *ctx, uint64_t *out, int64_t cap_ctas, int64_t *grid_out);
 
 /* ---- pinned host memory helpers ------------------------------------------- */
 void *cfmm_host_alloc(size_t bytes);

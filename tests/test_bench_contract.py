@@ -25,8 +25,12 @@ def test_roofline_object_single_kernel_step():
     prof = {0: (float(times.astype(np.float64).sum()), 1000), 1: (0.0, 0), 2: (0.0, 0), 3: (0.0, 0)}
     pt = {0: times, 1: np.zeros(0, np.float32), 2: np.zeros(0, np.float32)}
     r = bench.roofline_object(prof, pt, 67.5, 1000, 1000, "product", 10_000_000, 320e6, 6576.1,
-                              "measured", 325709824.0)
+                              "measured", "config5_10M_product_50k_tokens", False)
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"].startswith("product_sweep_tma")
+    # traffic: only from an ncu capture of THIS kernel on THIS workload (profiles/traffic.json), else null
+    assert r["traffic"] == bench.read_traffic("config5_10M_product_50k_tokens", "product_sweep_tma")
+    assert bench.read_traffic("config2_100k_product_1k_tokens", "sweep_kernel_univ3") is None
+    assert r["l2_state"] == "inputs larger than L2"
     assert abs(r["avg_launch_us"] - 71.978) < 0.01
     assert abs(r["achieved"] - 320e6 / (r["avg_launch_us"] * 1e-6) / 1e9) < 1e-6
     assert abs(r["frac"] - r["achieved"] / 6576.1) < 1e-12
@@ -42,7 +46,9 @@ def test_roofline_object_mixed_and_exchange():
     bench = _bench()
     prof = {0: (10.0, 100), 1: (30.0, 100), 2: (0.0, 0), 3: (1.2, 100)}
     pt = {0: np.full(100, 0.1, np.float32), 1: np.full(100, 0.3, np.float32), 2: np.zeros(0, np.float32)}
-    r = bench.roofline_object(prof, pt, 45.0, 100, 300, "mixed", 1_000_000, 40e6, 6650.0, "fallback", None)
+    r = bench.roofline_object(prof, pt, 45.0, 100, 300, "mixed", 1_000_000, 40e6, 6650.0, "fallback",
+                              "config3_1M_mixed_10k_tokens", True)
+    assert r["l2_state"].startswith("flushed")
     assert r["kernel"] == "sweep_kernel<GeomeanPools>"
     assert r["algorithmic_bytes_per_launch"] == 500_000 * 48
     assert "back_to_back" not in r          # several launches per step: no single-kernel figure

@@ -280,17 +280,17 @@ def test_inrange_math(cr):
     p.close()
 
 
-@pytest.mark.parametrize("variant,fixed,chunks", [(-1, 1, 14), (0, 1, 14), (0, 0, 14), (0, 1, 5), (0, 0, 1)])
-@pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7), (96, 2), (97, 1601)])
-def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, chunks, m, n):
-    """The b-bucketed TMA kernel with fixed-point and with fp64 slice partials, with
-    full and with short tiles (several buckets at n = 20011, one bucket at n = 7,
-    a single chunk, a chunk plus one pool in a second bucket), and the
-    first-generation kernel (-1)."""
+@pytest.mark.parametrize("variant,fixed,per_sm", [(-1, 1, 0), (0, 1, 0), (0, 0, 0), (0, 1, 1)])
+@pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7), (96, 2), (97, 1601), (40_000, 1601)])
+def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, per_sm, m, n):
+    """The b-bucketed TMA kernel with fixed-point and with fp64 slice partials, with two
+    and with one CTA per SM (several buckets at n = 20011, one bucket at n = 7, a single
+    chunk, two buckets with CTAs that straddle the boundary), and the first-generation
+    kernel (-1)."""
     R, g, Ai = synth.product_pools(m, n, seed=variant + 10)
     p = make_pools(cr, n, product=(R, g, Ai), pre={"tma_variant": variant})
     p.set_option("psi_fixed_point", fixed)
-    p.set_option("tile_chunks", chunks)
+    p.set_option("blocks_per_sm", per_sm)
     for kind in ("near", "wide"):
         v = synth.dual_prices(n, kind)
         Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
@@ -397,6 +397,68 @@ def test_device_resident_api(cr, oracle, synth):
         # read the context-owned buffer through torch: wrap the raw pointer
         check = _from_ptr(torch, ptr, n + 1, dev).clone().cpu().numpy()
         check_psi(oracle, A, D, L, v, n, check[:n], float(check[n]), R=np.concatenate([R, Rg]), g=np.concatenate([g, gg]))
+    p.close()
+
+
+def test_flat_pool_file_ingest(cr, oracle, synth, tmp_path):
+    """cfmm_add_pool_file == cfmm_add_product / cfmm_add_geomean on the same arrays (insertion
+    order across files and direct adds included); a file for another token count is refused."""
+    n = 700
+    R, g, Ai = synth.product_pools(30_000, n, seed=8)
+    Rg, gg, Ag, wg = synth.geomean_pools(5_000, n, seed=9)
+    cr.write_pool_file(tmp_path / "a.cfmm", n, R[:20_000], g[:20_000], Ai[:20_000])
+    cr.write_pool_file(tmp_path / "g.cfmm", n, Rg, gg, Ag, wg)
+    p = cr.DevicePools(n)
+    p.add_file(tmp_path / "a.cfmm")
+    p.add_file(tmp_path / "g.cfmm")
+    p.add_product(R[20_000:], g[20_000:], Ai[20_000:])
+    p.finalize()
+    q = make_pools(cr, n, product=(R, g, Ai), geomean=(Rg, gg, Ag, wg))
+    v = synth.dual_prices(n, "wide")
+    p.sweep(v, materialize=True)
+    q.sweep(v, materialize=True)
+    Dp, Lp = p.trades()
+    Dq, Lq = q.trades()
+    # p's insertion order: product[:20k], geomean, product[20k:];  q's: product, geomean
+    assert np.array_equal(Dp[:20_000], Dq[:20_000]) and np.array_equal(Dp[25_000:], Dq[20_000:30_000])
+    assert np.array_equal(Dp[20_000:25_000], Dq[30_000:]) and np.array_equal(Lp[20_000:25_000], Lq[30_000:])
+    Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+    assert np.array_equal(Dq[:30_000], Do) and np.array_equal(Lq[:30_000], Lo)
+    other = cr.DevicePools(n + 1)
+    with pytest.raises(cr.CFMMError):
+        other.add_file(tmp_path / "a.cfmm")
+    for x in (p, q, other):
+        x.close()
+
+
+def test_sweep_graph_replay(cr, oracle, synth):
+    """cfmm_sweep on the same pinned buffers: eager, then captured, then replayed as one
+    graph launch; ν changes between calls, options and reserve pushes invalidate the graphs,
+    materialising and device-resident sweeps interleave (both parities).  Every result is
+    checked against the oracle, and the launch counter keeps counting one kernel per replay."""
+    n = 3_001
+    R, g, Ai = synth.product_pools(150_000, n, seed=41)
+    p = make_pools(cr, n, product=(R, g, Ai))
+    rng = np.random.default_rng(0)
+    for it in range(14):
+        v = synth.dual_prices(n, ["near", "wide"][it % 2], seed=100 + it)
+        if it == 6:
+            p.set_option("gradient_math", 0)     # bumps the version: graphs are re-captured
+        if it == 9:
+            p.set_option("gradient_math", 1)
+            R = R.copy()
+            R[10:5000] *= 1.5
+            p.update_reserves(0, 10, R[10:5000])
+        if it == 11:
+            p.sweep(v, materialize=True)          # flips the accumulator parity only
+        Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
+        l0 = p.launch_count
+        psi, acc = p.sweep(v)
+        assert p.launch_count - l0 in (1, 2)      # one sweep kernel (+ a re-pack after option / reserve changes)
+        check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g)
+    p.set_option("sweep_graphs", 0)
+    psi2, acc2 = p.sweep(v)
+    check_psi(oracle, Ai, Do, Lo, v, n, psi2, acc2, R=R, g=g)
     p.close()
 
 

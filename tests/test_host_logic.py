@@ -1,6 +1,8 @@
 """Host-side logic that needs no GPU: objectives (test/objectives.jl), pool
 descriptors, sharding, and the Router/route! driver wired to an ORACLE-backed
 stand-in for DevicePools (tests may use the oracle; the product never does)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -178,3 +180,30 @@ def test_unknown_pool_type_rejected(cr):
         Ai = np.array([1, 2])
     with pytest.raises(TypeError):
         cr.Router(cr.LinearNonnegative(np.ones(2)), [Curve()], 2, _pools_factory=OraclePools)
+
+
+def test_flat_pool_file_roundtrip(cr, tmp_path):
+    """The flat ingest format (cfmm_pool_file_write / _info): header, sizes, rejection of
+    foreign or truncated files.  (Adding a file to a context needs a GPU: tests/test_gpu_parity.py.)"""
+    from cfmmrouter_b200 import synth
+    R, g, Ai = synth.product_pools(1000, 50, seed=1)
+    f = tmp_path / "p.cfmm"
+    cr.write_pool_file(f, 50, R, g, Ai)
+    assert cr.pool_file_info(f) == (0, 50, 1000)
+    assert os.path.getsize(f) == 64 + 1000 * 40
+    raw = np.fromfile(f, dtype=np.uint8)
+    assert bytes(raw[:8]) == b"CFMMPOOL"
+    body = raw[64:].view(np.float64)
+    assert np.array_equal(body[:2000].reshape(-1, 2), R) and np.array_equal(body[2000:3000], g)
+    assert np.array_equal(raw[64 + 24000:].view(np.int64).reshape(-1, 2), Ai)
+    Rg, gg, Ag, wg = synth.geomean_pools(10, 50, seed=2)
+    f2 = tmp_path / "g.cfmm"
+    cr.write_pool_file(f2, 50, Rg, gg, Ag, wg)
+    assert cr.pool_file_info(f2) == (1, 50, 10) and os.path.getsize(f2) == 64 + 10 * 56
+    bad = tmp_path / "bad.cfmm"
+    bad.write_bytes(raw[:-8].tobytes())          # truncated
+    with pytest.raises(OSError):
+        cr.pool_file_info(bad)
+    bad.write_bytes(b"NOTAPOOL" + raw[8:].tobytes())
+    with pytest.raises(OSError):
+        cr.pool_file_info(bad)

@@ -1,8 +1,7 @@
 """CPU tests of the device layout cfmm_finalize builds for ProductTwoCoin pools
 (csrc/pool_layout.hpp), through the device-free hook cfmm_debug_product_layout:
 b-bucketing, per-bucket padding to whole 96-pool chunks, a-order inside buckets,
-hub detection and degree orientation; and of the TMA kernel's tile schedule
-(cfmm_debug_tile_schedule): chunk-balanced CTA ranges, tiles inside one bucket."""
+hub detection and degree orientation."""
 import ctypes as C
 
 import numpy as np
@@ -75,41 +74,6 @@ def test_uniform_graph_layout(cr, m, n, variant):
         assert lay["bucketed"] and lay["tile"] == 96
         B = -(-n // 1600)
         assert lay["nb"] == -(-n // B) and lay["nb"] <= 1600
-
-
-def schedule(cr, chunk_bucket, grid, max_chunks=14):
-    lib = cr.load_library()
-    cb = np.ascontiguousarray(chunk_bucket, dtype=np.int32)
-    counts = np.zeros(2, dtype=np.int64)
-    i32, i64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
-    assert lib.cfmm_debug_tile_schedule(cb.ctypes.data_as(i32), len(cb), grid, max_chunks, 0, None, None,
-                                        counts.ctypes.data_as(i64)) == 0
-    tiles, g = int(counts[0]), int(counts[1])
-    desc = np.zeros((tiles, 4), dtype=np.int32)
-    start = np.zeros(g + 1, dtype=np.int32)
-    assert lib.cfmm_debug_tile_schedule(cb.ctypes.data_as(i32), len(cb), grid, max_chunks, tiles,
-                                        desc.ctypes.data_as(i32), start.ctypes.data_as(i32),
-                                        counts.ctypes.data_as(i64)) == 0
-    return desc, start, g
-
-
-@pytest.mark.parametrize("grid", [1, 3, 296, 5000])
-@pytest.mark.parametrize("sizes", [[1], [5, 1, 1, 40], [1000, 3, 2500, 17, 17, 900], [13021] * 8])
-def test_tile_schedule(cr, sizes, grid):
-    cb = np.repeat(np.arange(len(sizes)), sizes)
-    desc, start, g = schedule(cr, cb, grid)
-    C_ = len(cb)
-    assert g == min(grid, C_) and start[0] == 0 and start[-1] == len(desc)
-    assert np.all(np.diff(start) >= 1)                       # every CTA has work
-    first, cnt, bk = desc[:, 0], desc[:, 1], desc[:, 2]
-    assert first[0] == 0 and np.all(first[1:] == first[:-1] + cnt[:-1]) and first[-1] + cnt[-1] == C_
-    assert np.all((cnt >= 1) & (cnt <= 14))
-    for f, c, b in desc[:, :3]:
-        assert np.all(cb[f:f + c] == b)                      # a tile lies in one bucket
-    per_cta = np.array([cnt[start[i]:start[i + 1]].sum() for i in range(g)])
-    assert per_cta.max() - per_cta.min() <= 1                # balanced to one chunk
-    lo = np.array([first[start[i]] for i in range(g)])
-    assert np.array_equal(lo, (C_ * np.arange(g)) // g)
 
 
 def test_sparse_buckets_fall_back_to_a_sorted(cr):
