@@ -25,6 +25,15 @@ POOL_UNIV3 = 2
 
 COMM_HANDLE_BYTES = 128
 
+class SolveOpts(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("max_fun", C.c_int), ("pgtol", C.c_double), ("factr", C.c_double)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("fun_evals", C.c_int), ("status", C.c_int),
+                ("f", C.c_double), ("pg_norm", C.c_double), ("solve_ms", C.c_double)]
+
+
 # every symbol include/cfmm_b200.h declares: name -> (restype, argtypes)
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
@@ -47,6 +56,7 @@ SYMBOLS = {
     "cfmm_sweep_device": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "cfmm_sweep_device_view": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cfmm_get_trades": (C.c_int, [_ctx, _dp, _dp]),
+    "cfmm_solve": (C.c_int, [_ctx, _dp, _dp, _dp, _dp, C.POINTER(SolveOpts), _dp, C.POINTER(SolveInfo)]),
     "cfmm_update_reserves": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, _dp]),
     "cfmm_apply_trades": (C.c_int, [_ctx]),
     "cfmm_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),

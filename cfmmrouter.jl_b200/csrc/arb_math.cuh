@@ -245,15 +245,20 @@ __device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w
 // Every tick's BoundedProduct (src/cfmms.jl:272-278, built by compute_at_tick
 // :294-313) depends only on pool state (liquidity, tick prices, current price),
 // never on ν.  It is therefore evaluated ONCE at cfmm_finalize, on the host,
-// with the same IEEE operations in the same order, and stored per tick as
-//   td[0] = k            td[1] = R_1 + α      td[2] = R_2 + β     td[3] = R_1
-//   td[4] = R_2          td[5] = k/β − (R_1+α)   (δ_max, "upper" direction)
-//   td[6] = k/α − (R_2+β)  (δ_max of the flipped pool, "lower" direction)   td[7] = pad
+// with the same IEEE operations in the same order, and stored per tick as two
+// direction records of 64 bytes each, ordered so that a walk reads ONE 32-byte
+// sector per fully consumed tick and the second sector only for the tick it
+// stops in (round 1 stored one 64-byte record whose two sectors were both needed
+// for every visited tick: ncu showed 2.33x the algorithmic DRAM traffic):
+//   "upper" walk (towards lower prices), doubles 0..7 of the tick:
+//     [k, R_1+α, δmax↑ = k/β − (R_1+α), R_2 | R_2+β, 0, 0, 0]
+//   "lower" walk (the flipped pool, :289), doubles 8..15:
+//     [k, R_2+β, δmax↓ = k/α − (R_2+β), R_1 | R_1+α, 0, 0, 0]
 // so a visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
-constexpr int kTickStride = 8;
+constexpr int kTickStride = 16;
 
 // find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395.  Both walk directions
-// share one loop (the direction is data: index step and field selection), so a
+// share one loop (the direction is data: index step and record half), so a
 // warp whose lanes walk in different directions does not execute two loops.
 __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks,
                                            double current_price, int current_tick, double g,
@@ -269,31 +274,30 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const double price = __ddiv_rn(up ? p : 1.0, up ? g : __dmul_rn(g, p));
   const int step = up ? 1 : -1;
   const int last = up ? n_ticks : 1;
+  const double* rec0 = td + (up ? 0 : 8);
   bool initial = true;
   double dsum = 0.0, lsum = 0.0;
   for (int idx = current_tick; up ? (idx <= last) : (idx >= last); idx += step) {
-    const double* tk = td + (size_t)(idx - 1) * kTickStride;
-    const double2 a = __ldg(reinterpret_cast<const double2*>(tk));      // (k, R1+α)
+    const double2* tk = reinterpret_cast<const double2*>(rec0 + (size_t)(idx - 1) * kTickStride);
+    const double2 a = __ldg(tk);  // (k, t.R_1 + t.α) of the (flipped) tick
     const double k = a.x;
     if (k == 0.0) {  // is_empty_pool: skipped, not terminal (:354-357, :376-379)
       initial = false;
       continue;
     }
     // find_arb_pos (src/cfmms.jl:321-337) on the (flipped, :289) precomputed tick
-    const double2 b = __ldg(reinterpret_cast<const double2*>(tk) + 1);  // (R2+β, R1)
-    const double ra = up ? a.y : b.x;                                   // t.R_1 + t.α
-    double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), ra), l;
+    double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), a.y), l;
     if (d <= 0.0) {
       d = 0.0;
       l = 0.0;
     } else {
-      const double2 c = __ldg(reinterpret_cast<const double2*>(tk) + 2);  // (R2, δmax_up)
-      const double dmax = up ? c.y : __ldg(tk + 6);
-      if (d >= dmax) {
-        d = dmax;
-        l = up ? c.x : b.y;  // t.R_2
+      const double2 b = __ldg(tk + 1);  // (δ_max, t.R_2): same 32-byte sector as a
+      if (d >= b.x) {
+        d = b.x;
+        l = b.y;
       } else {
-        l = __dsub_rn(up ? b.x : a.y, __dsqrt_rn(__dmul_rn(price, k)));  // (R_2+β) − sqrt(price·k)
+        const double rb = __ldg(reinterpret_cast<const double*>(tk + 2));  // t.R_2 + t.β (second sector)
+        l = __dsub_rn(rb, __dsqrt_rn(__dmul_rn(price, k)));
       }
     }
     if (!initial && (d == 0.0 || l == 0.0)) break;  // :362, :384

@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -25,6 +26,7 @@
 #include "pool_layout.hpp"
 #include "sweep_kernels.cuh"
 #include "product_tma.cuh"
+#include "solver.cuh"
 
 namespace {
 
@@ -368,7 +370,9 @@ int upload_set(cfmm_ctx* ctx, int type) {
         volatile double rb = R2 + beta;
         volatile double dmax_up = k / beta - ra;
         volatile double dmax_dn = k / alpha - rb;
-        const double rec[cfmm::kTickStride] = {k, ra, rb, R1, R2, dmax_up, dmax_dn, 0.0};
+        // two direction records of one 32-byte sector + spill each (arb_math.cuh)
+        const double rec[cfmm::kTickStride] = {k, ra, dmax_up, R2, rb, 0.0, 0.0, 0.0,
+                                               k, rb, dmax_dn, R1, ra, 0.0, 0.0, 0.0};
         td.insert(td.end(), rec, rec + cfmm::kTickStride);
       }
       n_ticks_total += e - b;
@@ -541,10 +545,23 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
     ctx->fx_pending.mode = 0;  // consumed
   }
   ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
-  kern<<<grid, cfmm::kTmaThreads, cfmm::kTmaSmemBytes, st>>>(
-      s.d_packed.p, s.d_gam.p, s.buckets, s.nb, d_v, FIXED ? s.d_inv_scale.p : nullptr, d_psi,
-      (int)ctx->n_tokens, take_zero_pending(ctx), s.in_fast_range ? 1 : 0, ctx->exact, fx, sc,
-      ctx->d_trace.n ? ctx->d_trace.p : nullptr);
+  const unsigned char* a_packed = s.d_packed.p;
+  const double* a_gam = s.d_gam.p;
+  int a_nb = s.nb, a_n = (int)ctx->n_tokens, a_range = s.in_fast_range ? 1 : 0, a_flags = ctx->exact;
+  const double* a_scale = FIXED ? s.d_inv_scale.p : nullptr;
+  double* a_zero = take_zero_pending(ctx);
+  unsigned long long* a_trace = ctx->d_trace.n ? ctx->d_trace.p : nullptr;
+  if (fx.mode != 0) {
+    // the fused exchange meets at a grid-wide barrier: a COOPERATIVE launch makes the driver
+    // guarantee that every CTA is resident (or fail the launch) instead of inferring it
+    void* args[] = {&a_packed, &a_gam, &s.buckets, &a_nb, &d_v, &a_scale, &d_psi, &a_n, &a_zero,
+                    &a_range, &a_flags, &fx, &sc, &a_trace};
+    CU_TRY(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(cfmm::kTmaThreads),
+                                            args, cfmm::kTmaSmemBytes, st));
+  } else {
+    kern<<<grid, cfmm::kTmaThreads, cfmm::kTmaSmemBytes, st>>>(a_packed, a_gam, s.buckets, a_nb, d_v, a_scale, d_psi,
+                                                                a_n, a_zero, a_range, a_flags, fx, sc, a_trace);
+  }
   if (ctx->d_trace.n) ctx->trace_grid = grid;
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
@@ -1033,17 +1050,243 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   const double* res = nullptr;
   rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, materialize != 0, st, &res);
   if (rc != CFMM_OK) return rc;
+  // A peer that died leaves the exchange polling until its timeout (seconds): only a sweep that
+  // took that long looks at the error word.
+  const auto t_wait = std::chrono::steady_clock::now();
+  auto comm_ok = [&]() -> int {
+    if (!ctx->comm.attached()) return CFMM_OK;
+    if (std::chrono::steady_clock::now() - t_wait < std::chrono::seconds(1)) return CFMM_OK;
+    if (ctx->comm.timed_out())
+      return fail(ctx, CFMM_ERR_COMM, "peer exchange timed out: a rank of the group did not deliver its packets");
+    return CFMM_OK;
+  };
   if (contiguous) {
     // caller keeps [psi ; acc] contiguous: one D2H copy
     CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb + sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
-    return CFMM_OK;
+    return comm_ok();
   }
   CU_TRY(ctx, cudaMemcpyAsync(psi_out, res, nb, cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaMemcpyAsync(ctx->h_stage, res + ctx->n_tokens,
                               sizeof(double), cudaMemcpyDeviceToHost, st));
   CU_TRY(ctx, cudaStreamSynchronize(st));
   *acc_out = ctx->h_stage[0];
+  return comm_ok();
+}
+
+// ---- cfmm_solve: the outer iteration of route! on the device (solver.cuh) ----------------
+int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const double* upper,
+               const double* v0, const cfmm_solve_opts* opts_in, double* v_out, cfmm_solve_info* info) {
+  int rc = ready(ctx);
+  if (rc != CFMM_OK) return rc;
+  if (!lower || !v_out) return fail(ctx, CFMM_ERR_INVALID, "cfmm_solve: lower and v_out are required");
+  cfmm_solve_opts o;
+  o.max_iter = 15000;
+  o.max_fun = 15000;
+  o.pgtol = 1e-5;
+  o.factr = 1e1;
+  if (opts_in) o = *opts_in;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t n = ctx->n_tokens;
+  constexpr int M = cfmm::kSolverM, K = cfmm::kSolverK, NG = cfmm::kSolverGram;
+  for (int64_t i = 0; i < n; ++i)
+    if (!(lower[i] == lower[i]) || (upper && !(upper[i] >= lower[i])))
+      return fail(ctx, CFMM_ERR_INVALID, "cfmm_solve: bad bounds at token %lld", (long long)(i + 1));
+  // device state
+  DevBuf<double> vec, hist, red, box;
+  DevBuf<unsigned> ticket;
+  DevBuf<unsigned long long> pgbits;
+  CU_TRY(ctx, vec.alloc((size_t)6 * n));
+  CU_TRY(ctx, hist.alloc((size_t)2 * M * n));
+  CU_TRY(ctx, red.alloc((size_t)cfmm::kSolverMaxBlocks * NG + NG + 8));
+  CU_TRY(ctx, box.alloc((size_t)3 * n));
+  CU_TRY(ctx, ticket.alloc(1));
+  CU_TRY(ctx, pgbits.alloc(1));
+  CU_TRY(ctx, cudaMemsetAsync(hist.p, 0, (size_t)2 * M * n * sizeof(double), st));
+  CU_TRY(ctx, cudaMemsetAsync(ticket.p, 0, sizeof(unsigned), st));
+  CU_TRY(ctx, cudaMemsetAsync(vec.p, 0, (size_t)6 * n * sizeof(double), st));
+  cfmm::SolverVecs q;
+  q.n = n;
+  q.x = vec.p;
+  q.g = vec.p + n;
+  q.xt = vec.p + 2 * n;
+  q.gt = vec.p + 3 * n;
+  q.d = vec.p + 4 * n;
+  q.pg = vec.p + 5 * n;
+  q.S = hist.p;
+  q.Y = hist.p + (size_t)M * n;
+  q.partials = red.p;
+  q.scal = red.p + (size_t)cfmm::kSolverMaxBlocks * NG;
+  q.ticket = ticket.p;
+  CU_TRY(ctx, cudaMemcpyAsync(box.p, lower, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  q.lower = box.p;
+  q.upper = nullptr;
+  q.lin = nullptr;
+  if (upper) {
+    bool finite = false;
+    for (int64_t i = 0; i < n && !finite; ++i) finite = upper[i] < 1.0e300;
+    if (finite) {
+      CU_TRY(ctx, cudaMemcpyAsync(box.p + n, upper, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+      q.upper = box.p + n;
+    }
+  }
+  if (lin) {
+    CU_TRY(ctx, cudaMemcpyAsync(box.p + 2 * n, lin, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    q.lin = box.p + 2 * n;
+  }
+  {
+    std::vector<double> start((size_t)n, 1.0 / (double)n);  // route!'s default start, router.jl:62
+    if (v0) start.assign(v0, v0 + n);
+    CU_TRY(ctx, cudaMemcpyAsync(q.d, start.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));  // `start` leaves scope
+  }
+  int blocks = (int)((n + cfmm::kSolverThreads - 1) / cfmm::kSolverThreads);
+  if (blocks > cfmm::kSolverMaxBlocks) blocks = cfmm::kSolverMaxBlocks;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  cudaEventRecord(t0, st);
+
+  double h[NG + 8];
+  int fevals = 0;
+  auto evaluate = [&](double* f_out) -> int {  // sweep at xt, gt = lin + Ψ, f = linᵀxt + acc
+    const double* view = nullptr;
+    int r = enqueue_sweep(ctx, q.xt, nullptr, false, st, &view);
+    if (r != CFMM_OK) return r;
+    cfmm::solver_grad_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, view);
+    ctx->launches++;
+    cudaMemcpyAsync(h + NG, q.scal + NG, 5 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h + NG + 5, view + n, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "cfmm_solve: %s", cudaGetErrorString(e));
+    ++fevals;
+    *f_out = h[NG + 1] + h[NG + 5];
+    return CFMM_OK;
+  };
+  double W[K][K];
+  double pgnorm = 0.0;
+  auto commit = [&](int slot, int store) -> int {  // accept xt; W, |pg|_inf back
+    cudaMemsetAsync(pgbits.p, 0, sizeof(unsigned long long), st);
+    cfmm::solver_commit_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, slot, store, pgbits.p);
+    ctx->launches++;
+    unsigned long long bits = 0;
+    cudaMemcpyAsync(h, q.scal, NG * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bits, pgbits.p, sizeof(bits), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "cfmm_solve: %s", cudaGetErrorString(e));
+    int k = 0;
+    for (int r = 0; r < K; ++r)
+      for (int c = r; c < K; ++c) W[r][c] = W[c][r] = h[k++];
+    memcpy(&pgnorm, &bits, sizeof(double));
+    return CFMM_OK;
+  };
+
+  // x = P(v0); first evaluation
+  cfmm::solver_init_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, q.d);
+  ctx->launches++;
+  double f = 0.0;
+  if ((rc = evaluate(&f)) != CFMM_OK) return rc;
+  if ((rc = commit(0, 0)) != CFMM_OK) return rc;
+
+  int age[M];      // history slots, oldest first
+  int cnt = 0, head = 0, iter = 0, status = 2;
+  const double epsmch = 2.220446049250313e-16;
+  while (true) {
+    if (!(f == f)) { status = 5; break; }            // NaN objective
+    if (pgnorm <= o.pgtol) { status = 0; break; }
+    if (iter >= o.max_iter) { status = 2; break; }
+    if (fevals >= o.max_fun) { status = 3; break; }
+    // ---- two-loop recursion in coefficient space over B = [S Y pg] ------------------------
+    cfmm::SolverCoef cf;
+    for (int j = 0; j < K; ++j) cf.c[j] = 0.0;
+    cf.c[K - 1] = 1.0;
+    double t_init = 1.0;
+    if (cnt == 0) {
+      const double nrm = std::sqrt(W[K - 1][K - 1]);
+      t_init = nrm > 0.0 ? std::min(1.0, 1.0 / nrm) : 1.0;   // first step of length <= 1, like L-BFGS-B
+    } else {
+      double alpha[M], rho[M];
+      for (int a = cnt - 1; a >= 0; --a) {
+        const int j = age[a];
+        rho[a] = 1.0 / W[j][M + j];
+        double sq = 0.0;
+        for (int c = 0; c < K; ++c) sq += W[j][c] * cf.c[c];
+        alpha[a] = rho[a] * sq;
+        cf.c[M + j] -= alpha[a];
+      }
+      const int jn = age[cnt - 1];
+      const double gamma = W[jn][M + jn] / W[M + jn][M + jn];
+      for (int c = 0; c < K; ++c) cf.c[c] *= gamma;
+      for (int a = 0; a < cnt; ++a) {
+        const int j = age[a];
+        double yr = 0.0;
+        for (int c = 0; c < K; ++c) yr += W[M + j][c] * cf.c[c];
+        cf.c[j] += alpha[a] - rho[a] * yr;
+      }
+    }
+    cfmm::solver_direction_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, cf);
+    ctx->launches++;
+    // ---- Armijo backtracking along the projected path ------------------------------------
+    double t = t_init, f_new = f;
+    bool accepted = false, stalled = false;
+    for (int ls = 0; ls < 30 && fevals < o.max_fun; ++ls) {
+      cfmm::solver_trial_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, t);
+      ctx->launches++;
+      if ((rc = evaluate(&f_new)) != CFMM_OK) return rc;
+      const double gdx = h[NG + 0], step2 = h[NG + 2];
+      if (step2 == 0.0) { stalled = true; break; }   // the projected step does not move
+      if (gdx < 0.0 && f_new <= f + 1e-4 * gdx) { accepted = true; break; }
+      if (!(gdx < 0.0) && cnt > 0) break;             // not a descent direction: restart from −pg
+      t *= (f_new == f_new && f_new < 1e300) ? 0.5 : 0.1;
+    }
+    if (!accepted) {
+      if (cnt > 0 && !stalled) {  // drop the history and retry with steepest descent
+        cnt = 0;
+        continue;
+      }
+      status = stalled ? 1 : 4;
+      break;
+    }
+    // ---- accept: store (s, y), new Gram matrix / projected gradient --------------------------
+    const int slot = head;
+    if ((rc = commit(slot, 1)) != CFMM_OK) return rc;
+    // drop the slot's old pair from the age list, append the new one if its curvature is usable
+    int w = 0;
+    for (int a = 0; a < cnt; ++a)
+      if (age[a] != slot) age[w++] = age[a];
+    cnt = w;
+    const double sy = W[slot][M + slot], yy = W[M + slot][M + slot];
+    if (sy > 1e-10 * yy && yy > 0.0) {
+      age[cnt++] = slot;
+      head = (head + 1) % M;
+    }
+    ++iter;
+    const double f_old = f;
+    f = f_new;
+    if (f_old - f <= o.factr * epsmch * std::max(std::max(std::fabs(f_old), std::fabs(f)), 1.0)) {
+      status = 1;
+      break;
+    }
+  }
+  // final ν, and the trades at it (router.jl:106-107)
+  CU_TRY(ctx, cudaMemcpyAsync(v_out, q.x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  const double* view = nullptr;
+  if ((rc = enqueue_sweep(ctx, q.x, nullptr, true, st, &view)) != CFMM_OK) return rc;
+  cudaEventRecord(t1, st);
+  CU_TRY(ctx, cudaStreamSynchronize(st));
+  if (info) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    info->iterations = iter;
+    info->fun_evals = fevals;
+    info->status = status;
+    info->f = f;
+    info->pg_norm = pgnorm;
+    info->solve_ms = ms;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
   return CFMM_OK;
 }
 

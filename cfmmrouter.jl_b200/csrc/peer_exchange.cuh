@@ -8,8 +8,12 @@
 // {hi32 | epoch32}, {lo32 | epoch32} (8-byte stores are single-copy atomic, so a
 // word is either old or complete).  The receiver polls its own local memory
 // until both words of a packet carry the current epoch, then adds the value.
-// There is no flag, no fence and no grid barrier on the critical path: one
-// NVLink traversal, and the reduction runs as packets land.  Ranks are summed
+// There is no flag and no fence on the exchange's critical path: one NVLink traversal
+// per hop, and the reduction runs as packets land.  (The FUSED form, run in the tail of the
+// sweep kernel, is preceded by one grid-wide barrier: the local partial sums must be
+// complete before they are pushed.)  Every wait is bounded: a poll that sees no packet for
+// kPollTimeoutNs raises the context's error word and gives up, so a dead peer turns into
+// CFMM_ERR_COMM on the host instead of a hung GPU.  Ranks are summed
 // in rank order, so every rank ends with the bitwise-identical vector (the
 // replicated L-BFGS-B drivers stay in lock-step).
 //
@@ -36,6 +40,13 @@ namespace cfmm {
 
 constexpr int kMaxPeers = 16;
 constexpr int kExchangeThreads = 256;
+constexpr unsigned long long kPollTimeoutNs = 4000000000ull;  // 4 s: far beyond any healthy exchange
+
+__device__ __forceinline__ unsigned long long exch_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct PeerHandle {
   cudaIpcMemHandle_t ipc;  // 64 B
@@ -54,6 +65,7 @@ struct ExchangeView {
   int world, rank;
   int64_t slice;                      // two-shot: tokens owned per rank = ceil(len / world)
   int64_t gather_off;                 // two-shot: packet offset of the gathered-result area
+  unsigned* error;                    // device word raised when a poll times out (host: CFMM_ERR_COMM)
 };
 
 __device__ __forceinline__ void st_packet(ulonglong2* p, unsigned long long a, unsigned long long b) {
@@ -63,6 +75,28 @@ __device__ __forceinline__ ulonglong2 ld_packet(const ulonglong2* p) {
   ulonglong2 v;
   asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
+}
+
+// poll one packet until both words carry `tag`; false (and the error word raised) on timeout
+__device__ __forceinline__ bool poll_packet(const ExchangeView& x, const ulonglong2* q, unsigned long long tag,
+                                            ulonglong2* out) {
+  ulonglong2 v = ld_packet(q);
+  if ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) {
+    const unsigned long long t0 = exch_now_ns();
+    unsigned spins = 0;
+    do {
+      v = ld_packet(q);
+      if ((++spins & 1023u) == 0u) {
+        if (*reinterpret_cast<volatile unsigned*>(x.error)) return false;  // somebody already gave up
+        if (exch_now_ns() - t0 > kPollTimeoutNs) {
+          atomicExch(x.error, 1u);
+          return false;
+        }
+      }
+    } while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag);
+  }
+  *out = v;
+  return true;
 }
 
 // one-shot body for elements first, first+stride, ... (callable from any kernel)
@@ -91,8 +125,8 @@ __device__ __forceinline__ void peer_allreduce_oneshot_body(const ExchangeView& 
         continue;
       }
       const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * len + j);
-      ulonglong2 v = ld_packet(q);
-      while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+      ulonglong2 v;
+      if (!poll_packet(x, q, tag, &v)) return;
       s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
     }
     dst[j] = s;
@@ -130,8 +164,8 @@ __device__ __forceinline__ void peer_allreduce_twoshot_body(const ExchangeView& 
       st_packet(x.recv_peer[owner] + ((int64_t)(x.rank * 2 + par) * x.slice + i),
                 ((bits >> 32) << 32) | tag, ((bits & 0xffffffffull) << 32) | tag);
       const ulonglong2* q = x.recv_local + x.gather_off + (int64_t)par * len + j;
-      ulonglong2 v = ld_packet(q);
-      while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+      ulonglong2 v;
+      if (!poll_packet(x, q, tag, &v)) return;
       dst[j] = __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
     } else {
       double s = 0.0;
@@ -143,8 +177,8 @@ __device__ __forceinline__ void peer_allreduce_twoshot_body(const ExchangeView& 
           continue;
         }
         const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * x.slice + i);
-        ulonglong2 v = ld_packet(q);
-        while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) v = ld_packet(q);
+        ulonglong2 v;
+        if (!poll_packet(x, q, tag, &v)) return;
         s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
       }
       dst[j] = s;
@@ -190,6 +224,12 @@ class PeerExchange {
     return epoch_;
   }
   const ExchangeView& view() const { return view_; }
+  // true when some poll of an earlier exchange timed out (checked by the host after a sync)
+  bool timed_out() const {
+    unsigned h = 0;
+    if (!err_word_) return false;
+    return cudaMemcpy(&h, err_word_, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h != 0;
+  }
 
   bool export_handle(int64_t len, PeerHandle* out) {
     if (!base_) {
@@ -198,6 +238,8 @@ class PeerExchange {
       bytes_ = (size_t)(kMaxPeers + 1) * 2 * (size_t)len * sizeof(ulonglong2);
       if (!ok(cudaMalloc(&base_, bytes_), "cudaMalloc(exchange)")) return false;
       if (!ok(cudaMemset(base_, 0, bytes_), "cudaMemset(exchange)")) return false;
+      if (!ok(cudaMalloc(&err_word_, sizeof(unsigned)), "cudaMalloc(exchange error word)")) return false;
+      if (!ok(cudaMemset(err_word_, 0, sizeof(unsigned)), "cudaMemset(exchange error word)")) return false;
     }
     memset(out, 0, sizeof(*out));
     if (!ok(cudaIpcGetMemHandle(&out->ipc, base_), "cudaIpcGetMemHandle")) return false;
@@ -235,6 +277,7 @@ class PeerExchange {
     view_.recv_local = (ulonglong2*)base_;
     view_.slice = (len_ + world - 1) / world;
     view_.gather_off = (int64_t)kMaxPeers * 2 * len_;
+    view_.error = err_word_;
     two_shot_ = world > 2;
     for (int p = 0; p < world; ++p) {
       PeerHandle h;
@@ -293,6 +336,8 @@ class PeerExchange {
         opened_[p] = nullptr;
       }
     if (base_) cudaFree(base_);
+    if (err_word_) cudaFree(err_word_);
+    err_word_ = nullptr;
     base_ = nullptr;
     attached_ = false;
     world_ = 1;
@@ -305,6 +350,7 @@ class PeerExchange {
     return false;
   }
   void* base_ = nullptr;
+  unsigned* err_word_ = nullptr;
   void* opened_[kMaxPeers] = {};
   size_t bytes_ = 0;
   int64_t len_ = 0;

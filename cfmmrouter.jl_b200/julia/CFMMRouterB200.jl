@@ -12,6 +12,8 @@
 #     using CFMMRouterB200           # re-exports CFMMRouter's names
 #     r = B200Router(LinearNonnegative(c), pools, n)    # instead of Router(...)
 #     route!(r); netflows(r); r.Δs; r.Λs; r.v           # unchanged
+#     route!(r; optimizer=:device)                       # outer iteration on the GPU too (cfmm_solve)
+#     r = B200Router(obj, pools, n; devices=0:7)         # pools sharded over 8 GPUs of this process
 module CFMMRouterB200
 
 using CFMMRouter
@@ -43,24 +45,27 @@ mutable struct B200Router{O,T}
     Δs::Vector{AbstractVector{T}}
     Λs::Vector{AbstractVector{T}}
     v::Vector{T}
-    ctx::Ptr{Cvoid}
-    order::Vector{Int}      # library insertion order -> index into cfmms
-    ψ::Vector{T}            # Σ A_i(Λ_i − Δ_i) of the last sweep
+    ctx::Ptr{Cvoid}         # context of the first device (all of them when there is one)
+    order::Vector{Int}      # library insertion order -> index into cfmms (first device's shard first)
+    ψ::Vector{T}            # Σ A_i(Λ_i − Δ_i) of the last sweep: a view of PINNED memory (cfmm_host_alloc)
     acc::Base.RefValue{T}   # Σ ν[A_i]ᵀ(Λ_i − Δ_i) of the last sweep
+    ctxs::Vector{Ptr{Cvoid}}        # one context per device (multi-GPU: pools sharded in list order)
+    shard::Vector{UnitRange{Int}}   # positions of `order` each context holds
+    pin::Ptr{Float64}               # pinned staging: ν [n] | ψ [n] | acc [1], per context (n_ctx blocks)
 end
 
-# Router(objective, cfmms, n_tokens), src/router.jl:18-35: pack Vector{CFMM} -> SoA, upload.
-function B200Router(objective::O, cfmms::Vector{C}, n_tokens; device::Integer=0) where {T,O<:Objective,C<:CFMM{T}}
-    T === Float64 || throw(ArgumentError("libcfmm_b200 is fp64-only"))
+# One device context holding the pools cfmms[ids] (positions in the caller's list); returns
+# (ctx, order) with order = library insertion order -> position in the caller's list.
+function make_context(cfmms::Vector{C}, ids::AbstractVector{Int}, n_tokens, device::Integer) where {T,C<:CFMM{T}}
     out = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:cfmm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Int64), out, device, n_tokens)
     rc == 0 || throw(B200Error(rc, unsafe_string(ccall((:cfmm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
     ctx = out[]
     order = Int[]
-    prod = findall(c -> c isa ProductTwoCoin, cfmms)
-    geo = findall(c -> c isa GeometricMeanTwoCoin, cfmms)
-    uni = findall(c -> c isa UniV3, cfmms)
-    length(prod) + length(geo) + length(uni) == length(cfmms) ||
+    prod = [i for i in ids if cfmms[i] isa ProductTwoCoin]
+    geo = [i for i in ids if cfmms[i] isa GeometricMeanTwoCoin]
+    uni = [i for i in ids if cfmms[i] isa UniV3]
+    length(prod) + length(geo) + length(uni) == length(ids) ||
         throw(MethodError(find_arb!, (cfmms,)))    # what the reference would hit
     if !isempty(prod)
         R = Float64[c.R[j] for c in cfmms[prod] for j in 1:2]
@@ -92,26 +97,82 @@ function B200Router(objective::O, cfmms::Vector{C}, n_tokens; device::Integer=0)
         append!(order, uni)
     end
     chk(ctx, ccall((:cfmm_finalize, LIB), Cint, (Ptr{Cvoid},), ctx))
+    return ctx, order
+end
+
+# Router(objective, cfmms, n_tokens), src/router.jl:18-35: pack Vector{CFMM} -> SoA, upload.
+# devices: one GPU (default) or several of THIS process; the pool list is split into contiguous
+# shards, one context per device, and the contexts are joined through the NVLink peer exchange
+# (cfmm_comm_export / cfmm_comm_attach, same-process path: raw pointers + peer access), so
+# every context's sweep returns the global [ψ; acc].
+function B200Router(objective::O, cfmms::Vector{C}, n_tokens; device::Integer=0,
+                    devices::AbstractVector{<:Integer}=[device]) where {T,O<:Objective,C<:CFMM{T}}
+    T === Float64 || throw(ArgumentError("libcfmm_b200 is fp64-only"))
+    W = length(devices)
+    m = length(cfmms)
+    ctxs = Ptr{Cvoid}[]; order = Int[]; shard = UnitRange{Int}[]
+    for (k, dev) in enumerate(devices)
+        ids = (div(m * (k - 1), W) + 1):div(m * k, W)
+        ctx, ord = make_context(cfmms, collect(ids), n_tokens, dev)
+        push!(ctxs, ctx); push!(shard, (length(order) + 1):(length(order) + length(ord))); append!(order, ord)
+    end
+    if W > 1
+        handles = zeros(UInt8, 128 * W)                       # CFMM_COMM_HANDLE_BYTES per context
+        for k in 1:W
+            GC.@preserve handles chk(ctxs[k], ccall((:cfmm_comm_export, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}),
+                ctxs[k], pointer(handles, 128 * (k - 1) + 1)))
+        end
+        for k in 1:W
+            GC.@preserve handles chk(ctxs[k], ccall((:cfmm_comm_attach, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctxs[k], W, k - 1, handles))
+        end
+    end
+    # pinned staging per context: the library replays {H2D ν, sweep, D2H [ψ; acc]} as one CUDA
+    # graph on buffers it has seen twice (cfmm_b200.h, "sweep_graphs"); pageable Vectors cannot
+    pin = convert(Ptr{Float64}, ccall((:cfmm_host_alloc, LIB), Ptr{Cvoid}, (Csize_t,), 8 * (2n_tokens + 1) * W))
+    pin == C_NULL && throw(OutOfMemoryError())
+    ψ = unsafe_wrap(Array, pin + 8n_tokens, n_tokens)         # context 1's ψ block
     Δs = AbstractVector{T}[zeros(T, 2) for _ in cfmms]     # zerotrade, router.jl:23-26
     Λs = AbstractVector{T}[zeros(T, 2) for _ in cfmms]
     r = B200Router{O,T}(objective, convert(Vector{CFMM{T}}, cfmms), Δs, Λs, zeros(T, n_tokens),
-                        ctx, order, zeros(T, n_tokens), Ref(zero(T)))
-    finalizer(x -> ccall((:cfmm_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.ctx), r)
+                        ctxs[1], order, ψ, Ref(zero(T)), ctxs, shard, pin)
+    finalizer(r) do x
+        foreach(c -> ccall((:cfmm_destroy, LIB), Cvoid, (Ptr{Cvoid},), c), x.ctxs)
+        ccall((:cfmm_host_free, LIB), Cvoid, (Ptr{Cvoid},), x.pin)
+    end
     return r
 end
 
 # One dual-gradient sweep on the GPU: find_arb!(r, v) (router.jl:38-42) + both
 # folds (router.jl:79-83, 98-100).  materialize=true also refreshes r.Δs / r.Λs.
-function sweep!(r::B200Router{O,T}, v::Vector{T}; materialize::Bool=false) where {O,T}
-    GC.@preserve v chk(r.ctx, ccall((:cfmm_sweep, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Cint), r.ctx, v, r.ψ, r.acc, materialize ? 1 : 0))
+function sweep!(r::B200Router{O,T}, v::AbstractVector{T}; materialize::Bool=false) where {O,T}
+    n = length(r.v); W = length(r.ctxs); blk = 2n + 1
+    # ν into every context's pinned block, then one blocking cfmm_sweep per context.  With
+    # several contexts the calls MUST run concurrently (the fused exchange kernels wait for
+    # each other): one task per context on Julia's thread pool (start julia with -t >= W).
+    for k in 1:W
+        unsafe_copyto!(r.pin + 8blk * (k - 1), pointer(v), n)
+    end
+    rcs = zeros(Cint, W)
+    GC.@preserve v begin
+        @sync for k in 1:W
+            base = r.pin + 8blk * (k - 1)
+            Threads.@spawn rcs[k] = ccall((:cfmm_sweep, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                r.ctxs[k], base, base + 8n, base + 16n, materialize ? 1 : 0)
+        end
+    end
+    foreach(k -> chk(r.ctxs[k], rcs[k]), 1:W)
+    r.acc[] = unsafe_load(r.pin, 2n + 1)            # every context holds the bitwise-identical sum
     if materialize
-        m = length(r.order)
-        D = Vector{Float64}(undef, 2m); L = Vector{Float64}(undef, 2m)
-        chk(r.ctx, ccall((:cfmm_get_trades, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), r.ctx, D, L))
-        for (k, i) in enumerate(r.order)          # library order -> r.cfmms order
-            r.Δs[i][1] = D[2k-1]; r.Δs[i][2] = D[2k]
-            r.Λs[i][1] = L[2k-1]; r.Λs[i][2] = L[2k]
+        for k in 1:W
+            mk = length(r.shard[k])
+            D = Vector{Float64}(undef, 2mk); L = Vector{Float64}(undef, 2mk)
+            chk(r.ctxs[k], ccall((:cfmm_get_trades, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), r.ctxs[k], D, L))
+            for (j, i) in enumerate(r.order[r.shard[k]])   # library order -> r.cfmms order
+                r.Δs[i][1] = D[2j-1]; r.Δs[i][2] = D[2j]
+                r.Λs[i][1] = L[2j-1]; r.Λs[i][2] = L[2j]
+            end
         end
     end
     return nothing
@@ -121,7 +182,31 @@ find_arb!(r::B200Router, v) = sweep!(r, collect(Float64, v); materialize=true)
 
 # route!, src/router.jl:58-108, with the three find_arb!(r, v) call sites and the
 # two fold loops replaced by sweep!.  Everything else is the reference's code path.
-function route!(r::B200Router; v=nothing, verbose=false, m=5, factr=1e1, pgtol=1e-5, maxfun=15_000, maxiter=15_000)
+# cfmm_solve_opts / cfmm_solve_info of include/cfmm_b200.h
+struct SolveOpts; max_iter::Cint; max_fun::Cint; pgtol::Cdouble; factr::Cdouble; end
+mutable struct SolveInfo; iterations::Cint; fun_evals::Cint; status::Cint; f::Cdouble; pg_norm::Cdouble; solve_ms::Cdouble; end
+
+# f(ν) = linᵀν on the box for both objectives of the reference (src/objectives.jl:62-79, 106-129)
+linear_term(o::CFMMRouter.LinearNonnegative) = zero(o.c)
+linear_term(o::CFMMRouter.BasketLiquidation) = (l = copy(o.Δin); l[o.i] = 0; l)
+
+function route!(r::B200Router; v=nothing, verbose=false, m=5, factr=1e1, pgtol=1e-5, maxfun=15_000, maxiter=15_000,
+                optimizer::Symbol=:host)
+    if optimizer === :device       # the whole outer iteration on the GPU: only scalars cross PCIe
+        length(r.ctxs) == 1 || throw(ArgumentError("optimizer=:device drives one GPU"))
+        lin = linear_term(r.objective); lo = lower_limit(r.objective); up = upper_limit(r.objective)
+        v0 = isnothing(v) ? C_NULL : pointer(v)
+        info = SolveInfo(0, 0, 0, 0.0, 0.0, 0.0); opts = SolveOpts(maxiter, maxfun, pgtol, factr)
+        GC.@preserve lin lo up v chk(r.ctx, ccall((:cfmm_solve, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{SolveOpts}, Ptr{Float64}, Ref{SolveInfo}),
+            r.ctx, lin, lo, up, v0, opts, r.v, info))
+        mk = length(r.order); D = Vector{Float64}(undef, 2mk); L = Vector{Float64}(undef, 2mk)
+        chk(r.ctx, ccall((:cfmm_get_trades, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), r.ctx, D, L))
+        for (j, i) in enumerate(r.order)
+            r.Δs[i] .= (D[2j-1], D[2j]); r.Λs[i] .= (L[2j-1], L[2j])
+        end
+        return nothing
+    end
     optimizer = L_BFGS_B(length(r.v), 17)
     if isnothing(v)
         r.v .= ones(length(r.v)) / length(r.v)
@@ -179,19 +264,19 @@ function update_reserves!(r::B200Router)
     if any(c -> c isa UniV3, r.cfmms)
         sync_reserves!(r)                       # mixed set: push the two-coin reserves
     else
-        chk(r.ctx, ccall((:cfmm_apply_trades, LIB), Cint, (Ptr{Cvoid},), r.ctx))
+        foreach(c -> chk(c, ccall((:cfmm_apply_trades, LIB), Cint, (Ptr{Cvoid},), c)), r.ctxs)
     end
     return nothing
 end
 
 # The reference reads cfmm.R live on every sweep; push mutated reserves explicitly.
 function sync_reserves!(r::B200Router)
-    for (ptype, T) in ((0, ProductTwoCoin), (1, GeometricMeanTwoCoin))
-        ids = [i for i in r.order if r.cfmms[i] isa T]
+    for (k, ctx) in enumerate(r.ctxs), (ptype, T) in ((0, ProductTwoCoin), (1, GeometricMeanTwoCoin))
+        ids = [i for i in r.order[r.shard[k]] if r.cfmms[i] isa T]
         isempty(ids) && continue
         R = Float64[r.cfmms[i].R[j] for i in ids for j in 1:2]
-        chk(r.ctx, ccall((:cfmm_update_reserves, LIB), Cint,
-            (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), r.ctx, ptype, 0, length(ids), R))
+        chk(ctx, ccall((:cfmm_update_reserves, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}), ctx, ptype, 0, length(ids), R))
     end
 end
 

@@ -24,6 +24,11 @@ class Objective:
     def upper_limit(self):
         raise NotImplementedError
 
+    def linear_term(self):
+        """lin such that f(ν) = linᵀν on the box [lower_limit, upper_limit] (None: the objective is
+        not of that form and the device solver cannot be used)."""
+        return None
+
 
 class LinearNonnegative(Objective):
     """U(Ψ) = cᵀΨ − I(Ψ ≥ 0)  (src/objectives.jl:51-79)."""
@@ -43,6 +48,9 @@ class LinearNonnegative(Objective):
 
     def lower_limit(self):  # objectives.jl:78
         return self.c + 1e-8
+
+    def linear_term(self):  # f = 0 on the box
+        return np.zeros_like(self.c)
 
     def upper_limit(self):  # objectives.jl:79
         return np.full_like(self.c, np.inf)
@@ -73,6 +81,11 @@ class BasketLiquidation(Objective):
             g[self.i - 1] = 0.0
         else:
             g[:] = np.inf
+
+    def linear_term(self):  # f = Σ_{j≠i} Δin_j ν_j on the box (ν_i >= 1 there)
+        lin = self.delta_in.copy()
+        lin[self.i - 1] = 0.0
+        return lin
 
     def lower_limit(self):  # objectives.jl:123-128
         eps = np.sqrt(np.finfo(np.float64).eps)

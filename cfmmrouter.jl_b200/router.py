@@ -203,6 +203,29 @@ class DevicePools:
         self._chk(self._lib.cfmm_get_trades(self._ctx, _dp(D), _dp(L)))
         return D, L
 
+    def solve(self, lower, lin=None, upper=None, v0=None, pgtol=1e-5, factr=1e1, maxfun=15_000, maxiter=15_000):
+        """cfmm_solve: minimise linᵀν + Σ arb_i(ν) over the box on the device.  Returns (ν, info dict);
+        the trades at ν are materialised (trades())."""
+        n = self.n_tokens
+        lower = np.ascontiguousarray(lower, dtype=np.float64)
+        arrs = [lower]
+        def opt(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (n,):
+                raise ValueError(f"vector arguments must have length {n}")
+            arrs.append(a)
+            return _dp(a)
+        if lower.shape != (n,):
+            raise ValueError(f"lower must have length {n}")
+        opts = _lib.SolveOpts(int(maxiter), int(maxfun), float(pgtol), float(factr))
+        info = _lib.SolveInfo()
+        out = np.empty(n)
+        self._chk(self._lib.cfmm_solve(self._ctx, opt(lin), _dp(lower), opt(upper), opt(v0), C.byref(opts),
+                                       _dp(out), C.byref(info)))
+        return out, {k: getattr(info, k) for k, _ in _lib.SolveInfo._fields_}
+
     def apply_trades(self):
         """R <- R + γΔ − Λ on the device, from the last materialising sweep."""
         self._chk(self._lib.cfmm_apply_trades(self._ctx))
@@ -355,6 +378,11 @@ class Router:
             psi, acc = out[:-1].copy(), float(out[-1])
         self._psi, self._acc = psi, acc
         if materialize:
+            self._fetch_trades()
+
+    def _fetch_trades(self):
+        """r.Δs / r.Λs <- the trades of the last materialising sweep, in list order."""
+        if True:
             D, L = self._pools.trades()
             Dl = np.zeros_like(D)
             Ll = np.zeros_like(L)
@@ -413,9 +441,28 @@ class _NoObjective(Objective):
 
 
 def route(r: Router, v=None, verbose=False, m=5, factr=1e1, pgtol=1e-5,
-          maxfun=15_000, maxiter=15_000):
+          maxfun=15_000, maxiter=15_000, optimizer="host"):
     """route!(r; v, verbose, m, factr, pgtol, maxfun, maxiter) (src/router.jl:58-108).
-    Overwrites r.Δs, r.Λs and r.v."""
+    Overwrites r.Δs, r.Λs and r.v.
+
+    optimizer="host" (default): L-BFGS-B on the host (scipy), one device sweep per function /
+    gradient evaluation, as in the reference.  optimizer="device": the whole outer iteration runs
+    on the GPU (cfmm_solve: projected L-BFGS, m = 5; objectives of the form linᵀν on a box, which
+    both reference objectives are) and only scalars cross PCIe per evaluation; single GPU."""
+    if optimizer == "device":
+        lin = r.objective.linear_term()
+        if lin is None:
+            raise TypeError("the device solver needs an objective with linear_term()")
+        if r._world > 1:
+            raise NotImplementedError("optimizer='device' drives one GPU")
+        n = len(r.v)
+        x, info = r._pools.solve(r.objective.lower_limit(), lin=lin, upper=r.objective.upper_limit(),
+                                 v0=None if v is None else np.asarray(v, dtype=np.float64),
+                                 pgtol=pgtol, factr=factr, maxfun=maxfun, maxiter=maxiter)
+        r.v[:] = x
+        r._fetch_trades()
+        r.last_result = info
+        return None
     from scipy.optimize import minimize
 
     n = len(r.v)

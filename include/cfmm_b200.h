@@ -157,6 +157,31 @@ int cfmm_update_reserves(cfmm_ctx *ctx, int type, int64_t first, int64_t count,
  * Fails with CFMM_ERR_INVALID if the context holds UniV3 pools. */
 int cfmm_apply_trades(cfmm_ctx *ctx);
 
+/* ---- the outer iteration on the device ---------------------------
+ * Minimises the dual g(nu) = lin' nu + sum_i arb_i(nu) over the box lower <= nu <= upper
+ * -- route! (src/router.jl:58-108) for objectives of the form f(nu) = lin' nu on a box,
+ * which both objectives of the reference are (src/objectives.jl:62-79: lin = 0, lower =
+ * c + 1e-8; :106-129: lin = Delta_in with lin[i] = 0, lower = sqrt(eps), 1 + sqrt(eps) at
+ * i).  nu, the gradient, the L-BFGS history (m = 5) and the search direction stay in device
+ * memory; every function/gradient evaluation is one sweep plus vector kernels, and only a
+ * few scalars cross PCIe per evaluation.  The optimizer is a projected L-BFGS with Armijo
+ * backtracking, not the Fortran L-BFGS-B: same minimiser of the convex dual, different
+ * iterates.  On return v_out holds the final nu and the trades at it are materialised
+ * (cfmm_get_trades), as after route!.  lin and upper may be NULL (0 / +inf), v0 NULL =
+ * ones/n (router.jl:62).  status: 0 projected gradient <= pgtol, 1 relative decrease <=
+ * factr*eps or no further move, 2 max_iter, 3 max_fun, 4 line search failed, 5 NaN. */
+typedef struct {
+  int max_iter, max_fun;
+  double pgtol, factr;
+} cfmm_solve_opts;
+typedef struct {
+  int iterations, fun_evals, status;
+  double f, pg_norm, solve_ms;
+} cfmm_solve_info;
+int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const double *upper,
+               const double *v0, const cfmm_solve_opts *opts /* NULL = route!'s defaults */,
+               double *v_out, cfmm_solve_info *info /* may be NULL */);
+
 /* Tunables (none is needed for normal use).
  *   "exact"            1 = evaluate all four closed forms exactly as written in the
  *                      reference for every pool; 0 (default) = evaluate only the side that
