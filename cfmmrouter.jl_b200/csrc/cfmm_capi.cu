@@ -90,13 +90,15 @@ struct PoolSet {
   int packed_mode = -1;        // -1 = stale; else (econ ? 1 : 0) | (fixed ? 2 : 0)
   DevBuf<double> d_inv_scale, d_tok_sum;
   bool fixed_ok = false;       // every token fits the fixed-point rules (range, totals)
+  DevBuf<unsigned> d_steal;    // per-CTA chunk counters of the TMA kernel, two sets (launch parity)
+  unsigned long long tma_sweeps = 0;  // TMA launches of this set so far
   std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
     d_Ai.release(); d_tick.release(); d_gidx.release();
-    d_packed.release(); d_inv_scale.release(); d_tok_sum.release();
+    d_packed.release(); d_inv_scale.release(); d_tok_sum.release(); d_steal.release();
   }
 };
 
@@ -148,14 +150,13 @@ struct cfmm_ctx {
     double* seen_psi = nullptr;
     unsigned long long seen_version = ~0ull;
     int64_t launches = 0;            // kernel launches one replay stands for
-    int tma_delta = 0;               // TMA sweeps one replay stands for
-  } graphs[2][2];
+    int tma_delta[2] = {0, 0};       // TMA launches (ProductTwoCoin, GeometricMean) one replay stands for
+  } graphs[2][4];
   unsigned long long state_version = 1;
   int use_graphs = 1;
   const void* pinned_ok[2] = {nullptr, nullptr};  // host pointers already verified as pinned
-  DevBuf<unsigned> d_steal;     // TMA kernel: per-CTA chunk counters, two sets (sweep parity)
   int steal = 1;                // 1 = CTAs that drain their range take chunks from others
-  unsigned long long tma_sweeps = 0;
+  int geomean_tma = 1;          // gradient-only GeometricMean sweeps on the TMA kernel (0: first-generation kernel)
   // resident CTAs per SM of every kernel instantiation this context has launched.
   // Per context, not per process: cudaFuncSetAttribute (the > 48 KB dynamic shared
   // memory opt-in) acts on the current device only, and contexts of one process
@@ -251,7 +252,7 @@ inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kF
 cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m) {
   const bool product = type == CFMM_POOL_PRODUCT;
   cfmm::TileShape shape;
-  if (product && ctx->tma_variant >= 0) {
+  if ((product || type == CFMM_POOL_GEOMEAN) && ctx->tma_variant >= 0) {
     shape.tile = cfmm::kTmaChunk;
     shape.nbmax = cfmm::kTmaNbMax;
   }
@@ -326,16 +327,17 @@ int upload_set(cfmm_ctx* ctx, int type) {
     }
     s.in_fast_range = bad_range == 0;
     CU_TRY(ctx, s.d_R.upload(r));
-    if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
+    if (s.tma_ok) {
       int rc = refresh_scale(ctx, s);
       if (rc != CFMM_OK) return rc;
     }
   }
   if (type == CFMM_POOL_GEOMEAN) {
-    std::vector<double2> w((size_t)m);
-    for (int64_t p = 0; p < m; ++p) {
+    std::vector<double2> w((size_t)mp, make_double2(0.5, 0.5));  // (padding pools: any valid weights)
+#pragma omp parallel for schedule(static) if (mp > (1 << 16))
+    for (int64_t p = 0; p < mp; ++p) {
       const int64_t i = s.order[(size_t)p];
-      w[(size_t)p] = make_double2(s.w[2 * i], s.w[2 * i + 1]);
+      if (i >= 0) w[(size_t)p] = make_double2(s.w[2 * i], s.w[2 * i + 1]);
     }
     CU_TRY(ctx, s.d_w.upload(w));
   }
@@ -494,57 +496,58 @@ int refresh_scale(cfmm_ctx* ctx, PoolSet& s) {
 }
 
 // the packed stream of the mode this sweep runs in (rebuilt when the mode or the reserves changed)
+template <int POOL>
 int ensure_packed(cfmm_ctx* ctx, PoolSet& s, bool econ, bool fixed, cudaStream_t st) {
   const int mode = (econ ? 1 : 0) | (fixed ? 2 : 0);
   if (s.packed_mode == mode) return CFMM_OK;
-  const size_t bytes = (size_t)s.n_chunks * cfmm::kTmaChunkBytes;
+  const size_t bytes = (size_t)s.n_chunks * cfmm::tma_chunk_bytes<POOL>();
   if (s.d_packed.n != bytes) CU_TRY(ctx, s.d_packed.alloc(bytes));
   const int threads = 256;
+  // ProductTwoCoin's economized form streams 1/γ; GeometricMean always γ
   cfmm::pack_chunks_kernel<<<(unsigned)((s.m_padded + threads - 1) / threads), threads, 0, st>>>(
-      s.d_R.p, s.d_gam.p, s.d_Ai.p, s.m_padded, fixed ? s.d_inv_scale.p : nullptr, econ ? 1 : 0, s.d_packed.p);
+      s.d_R.p, s.d_gam.p, s.d_Ai.p, POOL == 1 ? s.d_w.p : nullptr, s.m_padded,
+      fixed ? s.d_inv_scale.p : nullptr, (POOL == 0 && econ) ? 1 : 0, cfmm::tma_chunk_bytes<POOL>(), s.d_packed.p);
   ctx->launches++;
   CU_TRY(ctx, cudaGetLastError());
   s.packed_mode = mode;
   return CFMM_OK;
 }
 
-template <bool ECON, bool SKEW, bool FIXED>
-int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
-                           cudaStream_t st) {
-  auto kern = cfmm::product_sweep_tma<ECON, SKEW, FIXED>;
+template <int POOL, bool ECON, bool SKEW, bool FIXED>
+int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, cudaStream_t st) {
+  auto kern = cfmm::product_sweep_tma<POOL, ECON, SKEW, FIXED>;
+  constexpr int kThreads = cfmm::tma_threads<POOL>(), kSmem = cfmm::tma_smem_bytes<POOL>();
   int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
-    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     cfmm::kTmaSmemBytes));
-    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cfmm::kTmaThreads,
-                                                              cfmm::kTmaSmemBytes));
+    CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
     if (occ < 1) return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma does not fit on an SM");
   }
-  int rc = ensure_packed(ctx, s, ECON, FIXED, st);
+  int rc = ensure_packed<POOL>(ctx, s, ECON, FIXED, st);
   if (rc != CFMM_OK) return rc;
   constexpr int kStealCtas = 2048;                             // CTAs per counter set
   constexpr int kStealCap = kStealCtas * cfmm::kStealStride;  // words per set
-  if (!ctx->d_steal.n) {
-    CU_TRY(ctx, ctx->d_steal.alloc(2 * kStealCap));
-    std::vector<unsigned> init(2 * kStealCap, (unsigned)(cfmm::kTmaPrimed * cfmm::kTmaWarps));
-    CU_TRY(ctx, cudaMemcpy(ctx->d_steal.p, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  if (!s.d_steal.n) {
+    CU_TRY(ctx, s.d_steal.alloc(2 * kStealCap));
+    std::vector<unsigned> init(2 * kStealCap, (unsigned)(cfmm::kTmaPrimed * cfmm::TmaShape<POOL>::kWarps));
+    CU_TRY(ctx, cudaMemcpy(s.d_steal.p, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
   }
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
   if (grid > s.n_chunks) grid = (int)s.n_chunks;
   if (grid > kStealCtas) grid = kStealCtas;
   cfmm::StealCtl sc;
-  sc.cnt = ctx->d_steal.p + (ctx->tma_sweeps & 1) * kStealCap;
-  sc.cnt_next = ctx->d_steal.p + ((ctx->tma_sweeps + 1) & 1) * kStealCap;
+  sc.cnt = s.d_steal.p + (s.tma_sweeps & 1) * kStealCap;
+  sc.cnt_next = s.d_steal.p + ((s.tma_sweeps + 1) & 1) * kStealCap;
   sc.enabled = ctx->steal;
-  ctx->tma_sweeps++;
+  s.tma_sweeps++;
   cfmm::FusedExchange fx = ctx->fx_pending;
   if (fx.mode != 0) {
     fx.target = ctx->grid_done_target + (unsigned long long)grid;
     fx.grid_done = ctx->d_grid_done.p;
     ctx->fx_pending.mode = 0;  // consumed
   }
-  ProfScope prof(ctx, CFMM_POOL_PRODUCT, st);
+  ProfScope prof(ctx, POOL == 0 ? CFMM_POOL_PRODUCT : CFMM_POOL_GEOMEAN, st);
   const unsigned char* a_packed = s.d_packed.p;
   const double* a_gam = s.d_gam.p;
   int a_nb = s.nb, a_n = (int)ctx->n_tokens, a_range = s.in_fast_range ? 1 : 0, a_flags = ctx->exact;
@@ -556,11 +559,11 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
     // guarantee that every CTA is resident (or fail the launch) instead of inferring it
     void* args[] = {&a_packed, &a_gam, &s.buckets, &a_nb, &d_v, &a_scale, &d_psi, &a_n, &a_zero,
                     &a_range, &a_flags, &fx, &sc, &a_trace};
-    CU_TRY(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(cfmm::kTmaThreads),
-                                            args, cfmm::kTmaSmemBytes, st));
+    CU_TRY(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kThreads),
+                                            args, kSmem, st));
   } else {
-    kern<<<grid, cfmm::kTmaThreads, cfmm::kTmaSmemBytes, st>>>(a_packed, a_gam, s.buckets, a_nb, d_v, a_scale, d_psi,
-                                                                a_n, a_zero, a_range, a_flags, fx, sc, a_trace);
+    kern<<<grid, kThreads, kSmem, st>>>(a_packed, a_gam, s.buckets, a_nb, d_v, a_scale, d_psi, a_n, a_zero,
+                                        a_range, a_flags, fx, sc, a_trace);
   }
   if (ctx->d_trace.n) ctx->trace_grid = grid;
   ctx->launches++;
@@ -570,20 +573,22 @@ int launch_product_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double*
   return CFMM_OK;
 }
 
-int launch_product_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi,
-                       cudaStream_t st) {
+template <int POOL>
+int launch_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, cudaStream_t st) {
   const bool econ = ctx->gradient_math != 0;
   const bool fixed = ctx->psi_fixed_point && s.fixed_ok;
 #define CFMM_TMA_CASE(E, K, F) \
-  if (econ == E && s.skewed == K && fixed == F) return launch_product_tma_cfg<E, K, F>(ctx, s, d_v, d_psi, st);
+  if (econ == E && s.skewed == K && fixed == F) return launch_tma_cfg<POOL, E, K, F>(ctx, s, d_v, d_psi, st);
   CFMM_TMA_CASE(true, false, true)
   CFMM_TMA_CASE(true, false, false)
-  CFMM_TMA_CASE(true, true, true)
-  CFMM_TMA_CASE(true, true, false)
   CFMM_TMA_CASE(false, false, true)
   CFMM_TMA_CASE(false, false, false)
-  CFMM_TMA_CASE(false, true, true)
-  CFMM_TMA_CASE(false, true, false)
+  if constexpr (POOL == 0) {  // hub orientation exists for the symmetric pool type only
+    CFMM_TMA_CASE(true, true, true)
+    CFMM_TMA_CASE(true, true, false)
+    CFMM_TMA_CASE(false, true, true)
+    CFMM_TMA_CASE(false, true, false)
+  }
 #undef CFMM_TMA_CASE
   return fail(ctx, CFMM_ERR_INVALID, "unreachable");
 }
@@ -620,7 +625,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     constexpr int PT = CFMM_POOL_PRODUCT;
     if (s.m > 0) {
       if (!mat && s.tma_ok && ctx->use_tma && ctx->debug_skip == 0) {
-        if ((rc = launch_product_tma(ctx, s, d_v, d_psi, st)) != CFMM_OK) return rc;
+        if ((rc = launch_tma<0>(ctx, s, d_v, d_psi, st)) != CFMM_OK) return rc;
       } else {
         cfmm::ProductPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p};
         if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
@@ -632,7 +637,9 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     constexpr int PT = CFMM_POOL_GEOMEAN;
     if (s.m > 0) {
       cfmm::GeomeanPools p{s.d_R.p, s.d_gam.p, s.d_Ai.p, s.d_w.p};
-      if (ctx->geomean_log2 && !mat) {
+      if (!mat && s.tma_ok && ctx->use_tma && ctx->geomean_tma && ctx->geomean_log2 && ctx->debug_skip == 0) {
+        if ((rc = launch_tma<1>(ctx, s, d_v, d_psi, st)) != CFMM_OK) return rc;
+      } else if (ctx->geomean_log2 && !mat) {
         cfmm::GeomeanPoolsLog2 q;
         static_cast<cfmm::GeomeanPools&>(q) = p;
         if ((rc = launch_sweep(ctx, PT, q, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
@@ -757,7 +764,6 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   for (auto& s : ctx->sets) s.release();
   ctx->d_nu.release();
   ctx->d_grid_done.release();
-  ctx->d_steal.release();
   ctx->d_trace.release();
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();
@@ -993,10 +999,13 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
                          ctx->debug_skip == 0;
   cfmm_ctx::SweepGraph* g = nullptr;
   if (graphable) {
-    g = &ctx->graphs[(ctx->epoch + 1) & 1][ctx->tma_sweeps & 1];
+    PoolSet& sp = ctx->sets[CFMM_POOL_PRODUCT];
+    PoolSet& sg = ctx->sets[CFMM_POOL_GEOMEAN];
+    g = &ctx->graphs[(ctx->epoch + 1) & 1][(sp.tma_sweeps & 1) | ((sg.tma_sweeps & 1) << 1)];
     if (g->exec && g->v == v && g->psi == psi_out && g->version == ctx->state_version) {
       ctx->epoch++;
-      ctx->tma_sweeps += (unsigned long long)g->tma_delta;
+      ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps += (unsigned long long)g->tma_delta[0];
+      ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps += (unsigned long long)g->tma_delta[1];
       ctx->launches += g->launches;
       ctx->events_recorded = false;
       CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
@@ -1009,7 +1018,7 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
       if (g->exec) cudaGraphExecDestroy(g->exec);
       g->exec = nullptr;
       const int64_t l0 = ctx->launches;
-      const unsigned long long t0 = ctx->tma_sweeps;
+      const unsigned long long t0 = ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps, t1 = ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps;
       cudaGraph_t graph = nullptr;
       CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       cudaError_t e = cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st);
@@ -1024,7 +1033,8 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
         g->psi = psi_out;
         g->version = ctx->state_version;
         g->launches = ctx->launches - l0;
-        g->tma_delta = (int)(ctx->tma_sweeps - t0);
+        g->tma_delta[0] = (int)(ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps - t0);
+        g->tma_delta[1] = (int)(ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps - t1);
         cudaGraphDestroy(graph);
         CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -1037,7 +1047,8 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
       g->exec = nullptr;
       ctx->use_graphs = 0;
       ctx->epoch--;
-      ctx->tma_sweeps = t0;
+      ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps = t0;
+      ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps = t1;
       ctx->launches = l0;
       if (rc != CFMM_OK) return rc;
     }
@@ -1381,7 +1392,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   d_pos.release();
   if (e != cudaSuccess)
     return fail(ctx, CFMM_ERR_CUDA, "update_reserves failed: %s", cudaGetErrorString(e));
-  if (type == CFMM_POOL_PRODUCT) return refresh_scale(ctx, s);
+  if (s.tma_ok) return refresh_scale(ctx, s);
   return CFMM_OK;
 }
 
@@ -1415,7 +1426,7 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
     flag.release();
     if (e != cudaSuccess) return fail(ctx, CFMM_ERR_CUDA, "apply_trades failed: %s", cudaGetErrorString(e));
     if (h) s.in_fast_range = false;  // later sweeps take the generic (guarded) form
-    if (t == CFMM_POOL_PRODUCT) {
+    if (s.tma_ok) {
       int rc2 = refresh_scale(ctx, s);
       if (rc2 != CFMM_OK) return rc2;
     }
@@ -1446,6 +1457,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->orient_by_degree = value < 0 ? -1 : (value != 0);
   } else if (!strcmp(key, "psi_fixed_point")) {
     ctx->psi_fixed_point = value != 0;
+  } else if (!strcmp(key, "geomean_tma")) {
+    ctx->geomean_tma = value != 0;
   } else if (!strcmp(key, "steal")) {
     ctx->steal = value != 0;
   } else if (!strcmp(key, "trace")) {

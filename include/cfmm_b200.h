@@ -217,6 +217,9 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *   "geomean_log2"     gradient-only GeometricMean sweeps take the power as exp2(e*log2 t)
  *                      (1, default; <= 12 ulp over the admitted range, validated against
  *                      pow on hardware) or as pow (0).
+ *   "geomean_tma"      1 (default) = gradient-only GeometricMeanTwoCoin sweeps run on the TMA
+ *                      kernel too (48-byte records, same fixed-point slice); 0 = first-generation
+ *                      kernel.
  *   "steal"            TMA kernel: 1 (default) = CTAs that finish their chunk range take chunks
  *                      from the ranges of slower CTAs; 0 = static ranges only.
  *   "trace"            1 = TMA sweeps record per-CTA phase timestamps (cfmm_debug_read_trace).

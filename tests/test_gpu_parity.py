@@ -203,10 +203,15 @@ def test_geomean_sweep_parity(cr, oracle, synth, m, n, exact):
         # gradient-only sweep: economized one-pow form (few ulp of the reserves) ...
         psi2, acc2 = p.sweep(v)
         check_psi(oracle, Ai, D, L, v, n, psi2, acc2, R=R, g=g)
+        # ... the same on the first-generation kernel (the default is the TMA kernel) ...
+        p.set_option("geomean_tma", 0)
+        psi4, acc4 = p.sweep(v)
+        check_psi(oracle, Ai, D, L, v, n, psi4, acc4, R=R, g=g)
+        p.set_option("geomean_tma", 1)
         # ... and the reference operation order
         p.set_option("gradient_math", 0)
         psi3, acc3 = p.sweep(v)
-        check_psi(oracle, Ai, D, L, v, n, psi3, acc3)
+        check_psi(oracle, Ai, D, L, v, n, psi3, acc3, Rq=R)
     p.close()
 
 
