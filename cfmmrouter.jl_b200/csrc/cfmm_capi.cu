@@ -1584,8 +1584,9 @@ int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t* Ai, in
 }
 
 // Measurement hook: the per-CTA phase timestamps (ns, %globaltimer) of the last TMA sweep
-// recorded under option "trace": out[8 * grid] = per CTA {entry, slice ready, chunk loop
-// done, partials flushed, grid barrier passed (fused exchange), exit, SM id, 0}.
+// recorded under option "trace": out[8 * grid] = per CTA {entry, slice ready, own range done,
+// all chunks done, partials flushed, exit, grid barrier passed (fused exchange), SM id << 32 |
+// chunks processed}.
 int cfmm_debug_read_trace(cfmm_ctx* ctx, uint64_t* out, int64_t cap_ctas, int64_t* grid_out) {
   if (!ctx || !grid_out) return CFMM_ERR_INVALID;
   if (!ctx->d_trace.n) return fail(ctx, CFMM_ERR_STATE, "option \"trace\" is off");

@@ -260,7 +260,8 @@ int cfmm_debug_product_layout(int64_t n_tokens, int64_t m, const int64_t *Ai, in
                               int32_t *chunk_bucket_out, uint8_t *swapped_out, int64_t *info);
 /* Measurement hook (option "trace" = 1): per-CTA phase timestamps of the last TMA gradient
  * sweep, ns of %globaltimer: out[8 * grid] = {entry, price slice ready, own range done,
- * all chunks done, partials flushed, exit, SM id, chunks processed} per CTA. */
+ * all chunks done, partials flushed, exit, grid barrier passed (fused exchange, else 0),
+ * SM id << 32 | chunks processed} per CTA. */
 int cfmm_debug_read_trace(cfmm_ctx *ctx, uint64_t *out, int64_t cap_ctas, int64_t *grid_out);
 
 /* ---- pinned host memory helpers ------------------------------------------- */

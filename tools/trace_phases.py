@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-CTA phase timeline of the TMA gradient sweep (measurement tool, option "trace"):
-%globaltimer stamps at CTA entry / slice ready / chunk loop done / flushed / exit, relative to
+%globaltimer stamps at CTA entry / slice ready / own range done / all chunks done / flushed /
+exit (and the chunks every CTA ended up processing: work stealing), relative to
 the first CTA's entry, plus the CUDA-event duration of the same launch.
 
     python tools/trace_phases.py [--m 10000000 --n 50000] [--json out.json]"""
@@ -56,18 +57,21 @@ def main():
         t = buf.reshape(-1, 8).astype(np.int64)
         t0 = t[:, 0].min()
         rel = (t[:, :6] - t0) / 1e3  # us
+        chunks = t[:, 7] & 0xffffffff
         rows.append({"event_us": e0.elapsed_time(e1) * 1e3,
                      "entry_max": rel[:, 0].max(), "entry_med": np.median(rel[:, 0]),
                      "slice_ready_med": np.median(rel[:, 1] - rel[:, 0]), "slice_ready_max": (rel[:, 1] - rel[:, 0]).max(),
-                     "loop_done_min": rel[:, 2].min(), "loop_done_med": np.median(rel[:, 2]), "loop_done_max": rel[:, 2].max(),
-                     "flush_med": np.median(rel[:, 3] - rel[:, 2]), "exit_max": rel[:, 5].max(),
-                     "loop_len_min": (rel[:, 2] - rel[:, 1]).min(), "loop_len_med": np.median(rel[:, 2] - rel[:, 1]),
-                     "loop_len_max": (rel[:, 2] - rel[:, 1]).max(), "grid": int(grid.value)})
+                     "loop_done_min": rel[:, 3].min(), "loop_done_med": np.median(rel[:, 3]), "loop_done_max": rel[:, 3].max(),
+                     "flush_med": np.median(rel[:, 4] - rel[:, 3]), "exit_max": rel[:, 5].max(),
+                     "loop_len_min": (rel[:, 3] - rel[:, 1]).min(), "loop_len_med": np.median(rel[:, 3] - rel[:, 1]),
+                     "loop_len_max": (rel[:, 3] - rel[:, 1]).max(), "grid": int(grid.value),
+                     "own_done_min": rel[:, 2].min(), "own_done_med": np.median(rel[:, 2]), "own_done_max": rel[:, 2].max(),
+                     "chunks_min": int(chunks.min()), "chunks_max": int(chunks.max())})
     med = {k: float(np.median([r[k] for r in rows])) for k in rows[0]}
     print(json.dumps(med, indent=1))
     # per-SM spread of the last rep: which SMs finish last
-    sm = t[:, 6]
-    done = rel[:, 2]
+    sm = t[:, 7] >> 32
+    done = rel[:, 3]
     order = np.argsort(done)
     print("slowest CTAs (sm, loop_done us):", [(int(sm[i]), round(float(done[i]), 1)) for i in order[-6:]])
     print("fastest CTAs (sm, loop_done us):", [(int(sm[i]), round(float(done[i]), 1)) for i in order[:6]])
