@@ -112,6 +112,8 @@ struct cfmm_ctx {
   bool has_trades = false;
   PoolSet sets[3];
   cudaStream_t stream = nullptr;
+  cudaStream_t last_stream = nullptr;  // stream of the last sweep (cfmm_sweep_device* may use the caller's)
+  cudaEvent_t ev_order = nullptr;      // orders work across a change of stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<double> d_nu;  // n
   double* h_stage = nullptr;   // pinned, n+1
@@ -397,6 +399,21 @@ int upload_set(cfmm_ctx* ctx, int type) {
   return CFMM_OK;
 }
 
+// Sweeps may be enqueued on a caller-supplied stream (cfmm_sweep_device*), everything else runs
+// on the context's own stream; the ping-pong accumulators, the trade buffers and the reserves
+// make consecutive operations dependent.  Whenever the stream changes, the new one waits for
+// the work enqueued on the previous one.
+int use_stream(cfmm_ctx* ctx, cudaStream_t st) {
+  if (ctx->last_stream && ctx->last_stream != st) {
+    cudaError_t e = cudaEventRecord(ctx->ev_order, ctx->last_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ctx->ev_order, 0);
+    if (e != cudaSuccess)
+      return fail(ctx, CFMM_ERR_CUDA, "stream ordering failed: %s", cudaGetErrorString(e));
+  }
+  ctx->last_stream = st;
+  return CFMM_OK;
+}
+
 // the first kernel of a sweep zeroes the other ping-pong accumulator
 inline double* take_zero_pending(cfmm_ctx* ctx) {
   double* p = ctx->zero_pending;
@@ -600,6 +617,10 @@ int launch_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, cuda
 // stays in the accumulator; *view receives the device pointer that holds it.
 int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
                   cudaStream_t st, const double** view) {
+  {
+    int rc0 = use_stream(ctx, st);
+    if (rc0 != CFMM_OK) return rc0;
+  }
   if (ctx->sweep_events) CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
   ctx->events_recorded = ctx->sweep_events != 0;
   ctx->epoch++;
@@ -733,6 +754,7 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
   CREATE_TRY(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   CREATE_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
   CREATE_TRY(cudaEventCreate(&ctx->ev0));
   CREATE_TRY(cudaEventCreate(&ctx->ev1));
   CREATE_TRY(ctx->d_nu.alloc((size_t)n_tokens));
@@ -768,6 +790,7 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1322,6 +1345,7 @@ int cfmm_get_trades(cfmm_ctx* ctx, double* Delta, double* Lambda) {
                 "no materialising sweep has run (call cfmm_sweep with materialize=1)");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   if (ctx->n_pools == 0) return CFMM_OK;
+  if ((rc = use_stream(ctx, ctx->stream)) != CFMM_OK) return rc;
   DevBuf<double2> allD, allL;
   CU_TRY(ctx, allD.alloc((size_t)ctx->n_pools));
   cudaError_t e = allL.alloc((size_t)ctx->n_pools);
@@ -1363,6 +1387,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   if (count == 0) return CFMM_OK;
   if (!R) return fail(ctx, CFMM_ERR_INVALID, "null reserve array");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  if ((rc = use_stream(ctx, ctx->stream)) != CFMM_OK) return rc;
   if (s.pos_of.empty()) {
     s.pos_of.resize((size_t)s.m);
     for (int64_t p = 0; p < s.m_padded; ++p)
@@ -1408,6 +1433,7 @@ int cfmm_apply_trades(cfmm_ctx* ctx) {
                 "ProductTwoCoin / GeometricMeanTwoCoin only)");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   ctx->state_version++;
+  if ((rc = use_stream(ctx, ctx->stream)) != CFMM_OK) return rc;
   DevBuf<int> flag;
   std::vector<int> zero(1, 0);
   for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) {

@@ -235,7 +235,11 @@ class DevicePools:
         self._chk(self._lib.cfmm_update_reserves(self._ctx, int(pool_type), int(first), len(R), _dp(R)))
 
     # -- multi-GPU --------------------------------------------------------------
-    def attach_group(self, group=None):
+    def detach_group(self):
+        self._chk(self._lib.cfmm_comm_detach(self._ctx))
+        self.peer_attached = False
+
+    def attach_group(self, group=None, barrier=True):
         """Join the NVLink peer exchange of a torch.distributed group (one
         process per GPU): export this rank's handle, all-gather the handles
         (torch.distributed is only the transport for 128 bytes per rank),
@@ -256,7 +260,8 @@ class DevicePools:
         allh = bytes(torch.cat(gathered).cpu().numpy().tobytes())
         self._chk(self._lib.cfmm_comm_attach(self._ctx, world, rank, allh))
         self.peer_attached = True
-        dist.barrier(group)
+        if barrier:
+            dist.barrier(group)
 
     def close(self):
         if self._ctx:
@@ -307,7 +312,9 @@ class Router:
 
     def __init__(self, objective: Objective, cfmms=None, n_tokens: int = None, *,
                  device: int = 0, group=None, exchange: str = "peer", _pools_factory=None):
-        if n_tokens is None:  # Router(objective, n_tokens), router.jl:36
+        if n_tokens is None and isinstance(cfmms, (int, np.integer)):
+            cfmms, n_tokens = None, int(cfmms)  # Router(objective, n_tokens): empty pool list, router.jl:36
+        if n_tokens is None:
             raise TypeError("n_tokens is required")
         self.objective = objective
         self.cfmms = list(cfmms) if cfmms is not None else []
@@ -326,9 +333,29 @@ class Router:
         self._pools = factory(int(n_tokens), device)
         self._upload()
         if self._world > 1 and exchange == "peer":
-            self._pools.attach_group(group)
+            self._attach_with_agreement(group)
         self._psi = np.zeros(int(n_tokens))
         self._acc = 0.0
+
+    def _attach_with_agreement(self, group):
+        """Join the NVLink peer exchange, or -- if ANY rank cannot (no P2P / IPC) -- fall back to
+        torch.distributed on every rank: a rank that raised alone would leave the others blocked in
+        their first exchange."""
+        import torch
+        import torch.distributed as dist
+        ok = 1
+        try:
+            self._pools.attach_group(group, barrier=False)
+        except _lib.CFMMError:
+            ok = 0
+        dev = torch.device("cuda", self._pools.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            if ok:
+                self._pools.detach_group()
+            self._exchange = "dist"
+        dist.barrier(group)
 
     # ascii aliases
     @property
@@ -373,8 +400,10 @@ class Router:
             import torch
             import torch.distributed as dist
             buf = torch.from_numpy(np.append(psi, acc))
+            if dist.get_backend(self._group) == "nccl":  # NCCL reduces device tensors only
+                buf = buf.to(torch.device("cuda", self._pools.device))
             dist.all_reduce(buf, group=self._group)
-            out = buf.numpy()
+            out = buf.cpu().numpy()
             psi, acc = out[:-1].copy(), float(out[-1])
         self._psi, self._acc = psi, acc
         if materialize:
@@ -525,6 +554,9 @@ def update_reserves(r: Router):
         if isinstance(c, (ProductTwoCoin, GeometricMeanTwoCoin)):
             c.R = c.R + c.gamma * D - L  # same operation order as the device kernel: bit-identical
     if any(isinstance(c, UniV3) for c in r.cfmms):
+        import warnings
+        warnings.warn("update_reserves: UniV3 pools keep their state (current_price / ticks are not advanced: "
+                      "the reference defines no reserve update for them)", stacklevel=2)
         r.sync_reserves()  # mixed set: push the two-coin reserves from the host objects
     else:
         r._pools.apply_trades()  # on the device, from the materialised trades: no upload

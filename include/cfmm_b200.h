@@ -126,7 +126,13 @@ int cfmm_sweep(cfmm_ctx *ctx, const double *v, double *psi_out,
 /* Same sweep with ν already resident in device memory and the result left
  * there: d_v [n_tokens], d_psi_acc [n_tokens + 1] = [psi ; acc], both device
  * pointers on the context's device.  Enqueued on `stream` (a cudaStream_t;
- * NULL = the context's own stream) WITHOUT synchronising. */
+ * NULL = the context's own stream) WITHOUT synchronising.  Stream rule: consecutive
+ * operations of a context depend on each other (ping-pong accumulators, trade buffers,
+ * reserves), so whenever an operation runs on a different stream than the previous one --
+ * another caller stream, or the context's own stream, which cfmm_sweep, cfmm_get_trades,
+ * cfmm_apply_trades, cfmm_update_reserves and cfmm_solve use -- the library makes the new
+ * stream wait (event) for the work enqueued on the previous one.  The caller only has to
+ * order its OWN reads of d_psi_acc after the sweep on `stream`. */
 int cfmm_sweep_device(cfmm_ctx *ctx, const double *d_v, double *d_psi_acc,
                       int materialize, void *stream);
 
