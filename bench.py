@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped)")
     ap.add_argument("--no-flush", action="store_true", help="small workloads: L2-warm timing only")
     ap.add_argument("--verify", type=int, default=1, help="N > 1: check the reduced [Psi; acc] (outside the timed regions)")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (measurement)")
     ap.add_argument("--strong", type=int, default=1, help="N > 1 (weak): also time the same total pool count split over the ranks")
     return ap.parse_args()
 
@@ -292,6 +293,8 @@ def run_ours(args):
                       "OpenMP, upload, device-side scale table) wall time on this rank"}
     pools.set_option("exact", args.exact)
     pools.set_option("sweep_events", 0)
+    for kv in args.opt:
+        pools.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     m_local = shard["m_local"]
     alg_bytes = float(shard["bytes"])
     # working sets that fit in the 126 MB L2 are timed with an L2 flush before every step

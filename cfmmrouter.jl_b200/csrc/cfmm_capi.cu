@@ -90,15 +90,24 @@ struct PoolSet {
   int packed_mode = -1;        // -1 = stale; else (econ ? 1 : 0) | (fixed ? 2 : 0)
   DevBuf<double> d_inv_scale, d_tok_sum;
   bool fixed_ok = false;       // every token fits the fixed-point rules (range, totals)
-  DevBuf<unsigned> d_steal;    // per-CTA chunk counters of the TMA kernel, two sets (launch parity)
-  unsigned long long tma_sweeps = 0;  // TMA launches of this set so far
+  // speed-weighted CTA ranges of the TMA kernel (product_tma.cuh): the table passed to the next
+  // launch, the smoothed per-CTA speed it was derived from, and the mapped pinned words the CTAs
+  // report their loop durations to (tagged with the table version they ran under)
+  cfmm::RangeTable ranges;
+  std::vector<double> speed;
+  unsigned* h_dur = nullptr;
+  unsigned range_version = 1;
+  int range_updates = 0;
+  int64_t tma_launches = 0;
   std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
     d_Ai.release(); d_tick.release(); d_gidx.release();
-    d_packed.release(); d_inv_scale.release(); d_tok_sum.release(); d_steal.release();
+    d_packed.release(); d_inv_scale.release(); d_tok_sum.release();
+    if (h_dur) cudaFreeHost(h_dur);
+    h_dur = nullptr;
   }
 };
 
@@ -135,6 +144,7 @@ struct cfmm_ctx {
   DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
+  int coop_launch = 1;            // fused exchange: launch the sweep kernel cooperatively (co-residency guaranteed)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived
@@ -152,12 +162,11 @@ struct cfmm_ctx {
     double* seen_psi = nullptr;
     unsigned long long seen_version = ~0ull;
     int64_t launches = 0;            // kernel launches one replay stands for
-    int tma_delta[2] = {0, 0};       // TMA launches (ProductTwoCoin, GeometricMean) one replay stands for
   } graphs[2][4];
   unsigned long long state_version = 1;
   int use_graphs = 1;
   const void* pinned_ok[2] = {nullptr, nullptr};  // host pointers already verified as pinned
-  int steal = 1;                // 1 = CTAs that drain their range take chunks from others
+  int balance = 1;              // 1 = TMA kernel: CTA ranges sized by measured CTA speed (feedback), 0 = even split
   int geomean_tma = 1;          // gradient-only GeometricMean sweeps on the TMA kernel (0: first-generation kernel)
   // resident CTAs per SM of every kernel instantiation this context has launched.
   // Per context, not per process: cudaFuncSetAttribute (the > 48 KB dynamic shared
@@ -542,22 +551,60 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   }
   int rc = ensure_packed<POOL>(ctx, s, ECON, FIXED, st);
   if (rc != CFMM_OK) return rc;
-  constexpr int kStealCtas = 2048;                             // CTAs per counter set
-  constexpr int kStealCap = kStealCtas * cfmm::kStealStride;  // words per set
-  if (!s.d_steal.n) {
-    CU_TRY(ctx, s.d_steal.alloc(2 * kStealCap));
-    std::vector<unsigned> init(2 * kStealCap, (unsigned)(cfmm::kTmaPrimed * cfmm::TmaShape<POOL>::kWarps));
-    CU_TRY(ctx, cudaMemcpy(s.d_steal.p, init.data(), init.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-  }
+  // (grid and range table)
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
   int grid = ctx->sm_count * per_sm;
   if (grid > s.n_chunks) grid = (int)s.n_chunks;
-  if (grid > kStealCtas) grid = kStealCtas;
-  cfmm::StealCtl sc;
-  sc.cnt = s.d_steal.p + (s.tma_sweeps & 1) * kStealCap;
-  sc.cnt_next = s.d_steal.p + ((s.tma_sweeps + 1) & 1) * kStealCap;
-  sc.enabled = ctx->steal;
-  s.tma_sweeps++;
+  // ---- speed-weighted ranges (see product_tma.cuh) ---------------------------------------
+  unsigned* d_dur = nullptr;
+  const bool balancing = ctx->balance && grid <= cfmm::kTmaMaxRanges && s.n_chunks >= (int64_t)grid * 32;
+  if (!balancing) {
+    s.ranges.n = 0;
+  } else {
+    if (!s.h_dur) {
+      CU_TRY(ctx, cudaHostAlloc((void**)&s.h_dur, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned), cudaHostAllocMapped));
+      memset(s.h_dur, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned));
+    }
+    CU_TRY(ctx, cudaHostGetDevicePointer((void**)&d_dur, s.h_dur, 0));
+    if (s.ranges.n != grid) {  // first launch with this grid: even split, neutral speeds
+      s.ranges.n = grid;
+      for (int g = 0; g <= grid; ++g) s.ranges.first[g] = (int)(s.n_chunks * g / grid);
+      s.speed.assign((size_t)grid, 1.0);
+      s.range_version = (s.range_version % 250) + 1;
+      s.range_updates = 0;
+    } else {
+      // has a launch under the CURRENT table reported from every CTA?  (the words carry the
+      // version of the table they were measured under: launches may still be in flight)
+      bool complete = true;
+      const volatile unsigned* hd = s.h_dur;
+      for (int g = 0; g < grid && complete; ++g) complete = (hd[g] >> 24) == s.range_version && (hd[g] & 0xffffffu) != 0;
+      if (complete) {
+        double total = 0.0;
+        for (int g = 0; g < grid; ++g) {
+          const double len = (double)(s.ranges.first[g + 1] - s.ranges.first[g]);
+          const double dur = (double)(hd[g] & 0xffffffu);
+          const double rel = len / dur;  // chunks per tick
+          s.speed[(size_t)g] = s.range_updates == 0 ? rel : 0.5 * s.speed[(size_t)g] + 0.5 * rel;
+          total += s.speed[(size_t)g];
+        }
+        // new boundaries: lengths proportional to speed, at least 2 * warps chunks each, exact total
+        double acc_len = 0.0;
+        int prev = 0;
+        for (int g = 0; g < grid; ++g) {
+          acc_len += (double)s.n_chunks * s.speed[(size_t)g] / total;
+          int end = g + 1 == grid ? (int)s.n_chunks : (int)(acc_len + 0.5);
+          const int min_end = prev + 1, max_end = (int)s.n_chunks - (grid - 1 - g);
+          end = end < min_end ? min_end : (end > max_end ? max_end : end);
+          s.ranges.first[g + 1] = end;
+          prev = end;
+        }
+        s.range_version = (s.range_version % 250) + 1;
+        s.range_updates++;
+      }
+    }
+  }
+  s.ranges.version = s.range_version;
+  s.tma_launches++;
   cfmm::FusedExchange fx = ctx->fx_pending;
   if (fx.mode != 0) {
     fx.target = ctx->grid_done_target + (unsigned long long)grid;
@@ -571,16 +618,16 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   const double* a_scale = FIXED ? s.d_inv_scale.p : nullptr;
   double* a_zero = take_zero_pending(ctx);
   unsigned long long* a_trace = ctx->d_trace.n ? ctx->d_trace.p : nullptr;
-  if (fx.mode != 0) {
+  if (fx.mode != 0 && ctx->coop_launch) {
     // the fused exchange meets at a grid-wide barrier: a COOPERATIVE launch makes the driver
     // guarantee that every CTA is resident (or fail the launch) instead of inferring it
     void* args[] = {&a_packed, &a_gam, &s.buckets, &a_nb, &d_v, &a_scale, &d_psi, &a_n, &a_zero,
-                    &a_range, &a_flags, &fx, &sc, &a_trace};
+                    &a_range, &a_flags, &fx, &s.ranges, &d_dur, &a_trace};
     CU_TRY(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kThreads),
                                             args, kSmem, st));
   } else {
     kern<<<grid, kThreads, kSmem, st>>>(a_packed, a_gam, s.buckets, a_nb, d_v, a_scale, d_psi, a_n, a_zero,
-                                        a_range, a_flags, fx, sc, a_trace);
+                                        a_range, a_flags, fx, s.ranges, d_dur, a_trace);
   }
   if (ctx->d_trace.n) ctx->trace_grid = grid;
   ctx->launches++;
@@ -1017,18 +1064,22 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   const bool contiguous = acc_out == psi_out + ctx->n_tokens;
 
   // ---- graph path: the whole call is one cudaGraphLaunch ---------------------------------
+  // (a graph freezes the kernel parameters, the range table among them: capture only once the
+  // speed feedback of the TMA kernels has settled)
+  bool settled = true;
+  for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) {
+    const PoolSet& ps = ctx->sets[t];
+    if (ps.m > 0 && ps.tma_ok && ctx->use_tma && ctx->balance && (ps.tma_launches == 0 || (ps.ranges.n != 0 && ps.range_updates < 6)))
+      settled = false;
+  }
   const bool graphable = ctx->use_graphs && !materialize && contiguous && !ctx->sweep_events &&
                          !ctx->comm.attached() && ctx->prof.type.empty() && !ctx->d_trace.n &&
-                         ctx->debug_skip == 0;
+                         ctx->debug_skip == 0 && settled;
   cfmm_ctx::SweepGraph* g = nullptr;
   if (graphable) {
-    PoolSet& sp = ctx->sets[CFMM_POOL_PRODUCT];
-    PoolSet& sg = ctx->sets[CFMM_POOL_GEOMEAN];
-    g = &ctx->graphs[(ctx->epoch + 1) & 1][(sp.tma_sweeps & 1) | ((sg.tma_sweeps & 1) << 1)];
+    g = &ctx->graphs[(ctx->epoch + 1) & 1][0];
     if (g->exec && g->v == v && g->psi == psi_out && g->version == ctx->state_version) {
       ctx->epoch++;
-      ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps += (unsigned long long)g->tma_delta[0];
-      ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps += (unsigned long long)g->tma_delta[1];
       ctx->launches += g->launches;
       ctx->events_recorded = false;
       CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
@@ -1041,7 +1092,6 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
       if (g->exec) cudaGraphExecDestroy(g->exec);
       g->exec = nullptr;
       const int64_t l0 = ctx->launches;
-      const unsigned long long t0 = ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps, t1 = ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps;
       cudaGraph_t graph = nullptr;
       CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       cudaError_t e = cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st);
@@ -1056,8 +1106,6 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
         g->psi = psi_out;
         g->version = ctx->state_version;
         g->launches = ctx->launches - l0;
-        g->tma_delta[0] = (int)(ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps - t0);
-        g->tma_delta[1] = (int)(ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps - t1);
         cudaGraphDestroy(graph);
         CU_TRY(ctx, cudaGraphLaunch(g->exec, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -1070,8 +1118,6 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
       g->exec = nullptr;
       ctx->use_graphs = 0;
       ctx->epoch--;
-      ctx->sets[CFMM_POOL_PRODUCT].tma_sweeps = t0;
-      ctx->sets[CFMM_POOL_GEOMEAN].tma_sweeps = t1;
       ctx->launches = l0;
       if (rc != CFMM_OK) return rc;
     }
@@ -1485,8 +1531,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->psi_fixed_point = value != 0;
   } else if (!strcmp(key, "geomean_tma")) {
     ctx->geomean_tma = value != 0;
-  } else if (!strcmp(key, "steal")) {
-    ctx->steal = value != 0;
+  } else if (!strcmp(key, "balance")) {
+    ctx->balance = value != 0;
   } else if (!strcmp(key, "trace")) {
     // measurement only: 1 = every TMA sweep records per-CTA phase timestamps (cfmm_debug_read_trace)
     cudaSetDevice(ctx->device);
@@ -1499,6 +1545,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     }
   } else if (!strcmp(key, "fused_exchange")) {
     ctx->fused_exchange = value != 0;
+  } else if (!strcmp(key, "coop_launch")) {
+    ctx->coop_launch = value != 0;
   } else if (!strcmp(key, "exchange_bypass")) {
     ctx->exchange_bypass = value != 0;
   } else if (!strcmp(key, "exchange_two_shot")) {

@@ -211,6 +211,9 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *   "blocks_per_sm"    resident CTAs per SM of the persistent kernels (measurement knob).
  *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
  *                      in the sweep kernel's tail; 0 = separate exchange launch.
+ *   "coop_launch"      multi-GPU: 1 (default) = the fused sweep+exchange kernel is launched with
+ *                      cudaLaunchCooperativeKernel (its grid barrier needs every CTA resident);
+ *                      0 = plain launch (residency inferred from the occupancy query).
  *   "exchange_bypass"  multi-GPU: 1 = sweeps skip the exchange and return this rank's partial
  *                      [psi ; acc] (verification; every rank must set it alike).
  *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol
@@ -226,8 +229,9 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *   "geomean_tma"      1 (default) = gradient-only GeometricMeanTwoCoin sweeps run on the TMA
  *                      kernel too (48-byte records, same fixed-point slice); 0 = first-generation
  *                      kernel.
- *   "steal"            TMA kernel: 1 (default) = CTAs that finish their chunk range take chunks
- *                      from the ranges of slower CTAs; 0 = static ranges only.
+ *   "balance"          TMA kernel: 1 (default) = every CTA's chunk range is sized by its measured
+ *                      speed (SMs differ by ~15 %; durations are fed back through mapped pinned
+ *                      memory and the range table is re-derived between launches); 0 = even split.
  *   "trace"            1 = TMA sweeps record per-CTA phase timestamps (cfmm_debug_read_trace).
  *   "profile"          N = time the next N kernel launches (cfmm_profile_read). */
 int cfmm_set_option(cfmm_ctx *ctx, const char *key, int64_t value);

@@ -18,7 +18,7 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/$
 kill $SMI
 python tools/trace_phases.py --json gpurun_out/${tag}_trace_10M.json > gpurun_out/${tag}_trace.log 2>&1
 python tools/trace_phases.py --m 1250000 --json gpurun_out/${tag}_trace_1250k.json >> gpurun_out/${tag}_trace.log 2>&1
-python tools/trace_phases.py --opt steal=0 --json gpurun_out/${tag}_trace_10M_nosteal.json >> gpurun_out/${tag}_trace.log 2>&1
+python tools/trace_phases.py --opt balance=0 --json gpurun_out/${tag}_trace_10M_nobalance.json >> gpurun_out/${tag}_trace.log 2>&1
 cat gpurun_out/${tag}_trace.log
 # ncu: launch list of the bench command, then one full capture per kernel family
 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_under_ncu.log 2>&1
