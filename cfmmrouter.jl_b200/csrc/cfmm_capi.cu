@@ -1230,6 +1230,7 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
 
   double h[NG + 8];
   int fevals = 0;
+  const double epsmch = 2.220446049250313e-16;
   auto evaluate = [&](double* f_out) -> int {  // sweep at xt, gt = lin + Ψ, f = linᵀxt + acc
     const double* view = nullptr;
     int r = enqueue_sweep(ctx, q.xt, nullptr, false, st, &view);
@@ -1271,7 +1272,6 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
 
   int age[M];      // history slots, oldest first
   int cnt = 0, head = 0, iter = 0, status = 2;
-  const double epsmch = 2.220446049250313e-16;
   while (true) {
     if (!(f == f)) { status = 5; break; }            // NaN objective
     if (pgnorm <= o.pgtol) { status = 0; break; }
@@ -1308,6 +1308,10 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
     cfmm::solver_direction_kernel<<<blocks, cfmm::kSolverThreads, 0, st>>>(q, cf);
     ctx->launches++;
     // ---- Armijo backtracking along the projected path ------------------------------------
+    // f is a sum of ~m terms of mixed sign: differences below ~8 eps |f| are rounding noise, and
+    // near the (very flat) optimum of a large market every useful step is that small -- a
+    // plain Armijo test would reject them all.  The slack admits them; pgtol / factr decide when
+    // to stop.
     double t = t_init, f_new = f;
     bool accepted = false, stalled = false;
     for (int ls = 0; ls < 30 && fevals < o.max_fun; ++ls) {
@@ -1316,9 +1320,17 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
       if ((rc = evaluate(&f_new)) != CFMM_OK) return rc;
       const double gdx = h[NG + 0], step2 = h[NG + 2];
       if (step2 == 0.0) { stalled = true; break; }   // the projected step does not move
-      if (gdx < 0.0 && f_new <= f + 1e-4 * gdx) { accepted = true; break; }
+      const double noise = 8.0 * epsmch * std::max(std::max(std::fabs(f), std::fabs(f_new)), 1.0);
+      if (gdx < 0.0 && f_new <= f + 1e-4 * gdx + noise) { accepted = true; break; }
       if (!(gdx < 0.0) && cnt > 0) break;             // not a descent direction: restart from −pg
-      t *= (f_new == f_new && f_new < 1e300) ? 0.5 : 0.1;
+      if (f_new == f_new && f_new < 1e300 && gdx < 0.0) {
+        // minimiser of the quadratic through f, the slope gdx (per unit t) and f_new, kept in [0.1 t, 0.5 t]
+        const double slope = gdx / t, denom = 2.0 * (f_new - f - gdx);
+        double tq = denom > 0.0 ? -slope * t * t / denom : 0.5 * t;
+        t = std::min(0.5 * t, std::max(0.1 * t, tq));
+      } else {
+        t *= 0.1;
+      }
     }
     if (!accepted) {
       if (cnt > 0 && !stalled) {  // drop the history and retry with steepest descent

@@ -23,9 +23,11 @@ def test_device_route_readme_quickstart(cr):
     r = cr.Router(cr.LinearNonnegative(np.ones(2)), pools, 2)
     cr.route(r, optimizer="device")
     psi = cr.netflows(r)
-    assert np.all(r.Δs >= -TOL) and np.all(r.Λs >= -TOL) and np.all(psi >= -TOL)
+    # (with R = 1e6 the dual is so flat that its stopping test, relative decrease <= 10 eps, admits
+    # |Ψ_1| up to ~1e-3 -- the host path's README test uses the same 1e-3 -- hence not TOL here)
+    assert np.all(r.Δs >= -TOL) and np.all(r.Λs >= -TOL) and np.all(psi >= -1e-3), (psi, r.last_result)
     check_dual_feasibility(r)
-    assert abs(psi[1] - 171.40) < 0.05 and abs(psi[0]) < 1e-3  # SURVEY App. B (README.md:27-39)
+    assert abs(psi[1] - 171.40) < 0.05 and abs(psi[0]) < 1e-3, (psi, r.last_result)  # SURVEY App. B (README.md:27-39)
     assert r.last_result["status"] in (0, 1) and r.last_result["fun_evals"] >= r.last_result["iterations"]
 
 
