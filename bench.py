@@ -423,6 +423,10 @@ def run_ours(args):
         barrier()
         e2e_s = time.perf_counter() - t0
 
+        # ---- per-phase timeline of the fused sweep+exchange kernel on rank 0 (%globaltimer stamps of
+        # every CTA; measurement option "trace", outside the timed regions) ---------------------
+        if world > 1 and exchange == "peer" and WORKLOADS[args.workload][2] == "product":
+            extra["phases_rank0_us"] = phase_trace(pools, step, barrier, rank)
         # ---- N > 1, outside every timed region: is the reduced [Ψ; acc] right? --------------
         if world > 1 and args.verify and exchange == "peer":
             extra["parity_checked"], extra["parity"] = verify_reduction(
@@ -507,6 +511,35 @@ def _view(torch, ptr, count, dev):
     h = _H()
     h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
     return torch.as_tensor(h, device=dev)
+
+
+def phase_trace(pools, step, barrier, rank):
+    """Median over 8 sweeps of the kernel's phases on this rank, from the per-CTA %globaltimer stamps:
+    chunk loop done (slowest CTA), partials flushed, grid barrier passed, exit (exchange done)."""
+    pools.set_option("trace", 1)
+    rows = []
+    for _ in range(8):
+        barrier()
+        step()
+        barrier()
+        grid = ctypes.c_int64()
+        pools._lib.cfmm_debug_read_trace(pools._ctx, None, 0, ctypes.byref(grid))
+        buf = np.zeros(max(int(grid.value), 1) * 8, dtype=np.uint64)
+        rc = pools._lib.cfmm_debug_read_trace(pools._ctx, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                              grid.value, ctypes.byref(grid))
+        if rc != 0 or grid.value == 0:
+            break
+        t = buf.reshape(-1, 8).astype(np.int64)
+        t0 = t[:, 0].min()
+        rel = lambda col: (t[:, col] - t0) / 1e3
+        rows.append({"slice_ready_med": float(np.median(rel(1))), "chunk_loop_done_med": float(np.median(rel(3))),
+                     "chunk_loop_done_max": float(rel(3).max()), "flushed_max": float(rel(4).max()),
+                     "grid_barrier_passed_med": float(np.median(rel(6))) if t[:, 6].any() else None,
+                     "exit_max": float(rel(5).max())})
+    pools.set_option("trace", 0)
+    if not rows or rank != 0:
+        return None
+    return {k: (float(np.median([r[k] for r in rows])) if rows[0][k] is not None else None) for k in rows[0]}
 
 
 def verify_reduction(torch, dist, pools, shard, nu_host, d_nu, sptr, n, dev, rank, world):

@@ -87,7 +87,11 @@ struct PoolSet {
   // stream (built lazily for the mode a sweep asks for) and the per-token 2^-s_b table of
   // the fixed-point Ψ[b] slice
   DevBuf<unsigned char> d_packed;
-  int packed_mode = -1;        // -1 = stale; else (econ ? 1 : 0) | (fixed ? 2 : 0)
+  int packed_mode = -1;        // -1 = stale; else (econ ? 1 : 0) | (fixed ? 2 : 0) | (compact ? 4 : 0)
+  // compact stream: γ dictionary (<= 256 distinct fees) and the per-pool codes (device order)
+  DevBuf<unsigned short> d_gcode;
+  DevBuf<double> d_gtab;       // [256] 1/γ by code, then [256] γ by code
+  bool compact_ok = false;
   DevBuf<double> d_inv_scale, d_tok_sum;
   bool fixed_ok = false;       // every token fits the fixed-point rules (range, totals)
   // speed-weighted CTA ranges of the TMA kernel (product_tma.cuh): the table passed to the next
@@ -95,7 +99,12 @@ struct PoolSet {
   // report their loop durations to (tagged with the table version they ran under)
   cfmm::RangeTable ranges;
   std::vector<double> speed;
-  unsigned* h_dur = nullptr;
+  DevBuf<unsigned> d_dur;      // per-CTA loop durations of the latest launch (device)
+  unsigned* h_dur = nullptr;   // pinned landing zone of the occasional D2H copy of d_dur
+  cudaEvent_t ev_dur = nullptr;
+  bool dur_pending = false;    // a copy is in flight (ev_dur)
+  bool balancing = false;      // the last TMA launch ran with speed feedback on
+  int since_copy = 0;
   unsigned range_version = 1;
   int range_updates = 0;
   int64_t tma_launches = 0;
@@ -105,9 +114,12 @@ struct PoolSet {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
     d_gam.release(); d_cp.release(); d_tickdata.release();
     d_Ai.release(); d_tick.release(); d_gidx.release();
-    d_packed.release(); d_inv_scale.release(); d_tok_sum.release();
+    d_packed.release(); d_inv_scale.release(); d_tok_sum.release(); d_gcode.release(); d_gtab.release();
     if (h_dur) cudaFreeHost(h_dur);
     h_dur = nullptr;
+    if (ev_dur) cudaEventDestroy(ev_dur);
+    ev_dur = nullptr;
+    d_dur.release();
   }
 };
 
@@ -165,9 +177,11 @@ struct cfmm_ctx {
   } graphs[2][4];
   unsigned long long state_version = 1;
   int use_graphs = 1;
+  bool capturing = false;  // cfmm_sweep is recording a graph: no event queries / side copies
   const void* pinned_ok[2] = {nullptr, nullptr};  // host pointers already verified as pinned
   int balance = 1;              // 1 = TMA kernel: CTA ranges sized by measured CTA speed (feedback), 0 = even split
   int geomean_tma = 1;          // gradient-only GeometricMean sweeps on the TMA kernel (0: first-generation kernel)
+  int compact_stream = 1;       // ProductTwoCoin, economized math: 24-byte pool records (γ dictionary) when the set allows it
   // resident CTAs per SM of every kernel instantiation this context has launched.
   // Per context, not per process: cudaFuncSetAttribute (the > 48 KB dynamic shared
   // memory opt-in) acts on the current device only, and contexts of one process
@@ -322,6 +336,39 @@ int upload_set(cfmm_ctx* ctx, int type) {
   }
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
+  s.compact_ok = false;
+  if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
+    // γ dictionary of the compact stream: fees are categorical in practice
+    std::vector<double> vals;
+    std::vector<unsigned short> code((size_t)mp, 0);
+    bool ok = true;
+    double last = std::nan("");
+    unsigned short last_code = 0;
+    for (int64_t p = 0; p < mp && ok; ++p) {
+      const double g = gam[(size_t)p];
+      if (g != last) {
+        size_t k = 0;
+        while (k < vals.size() && vals[k] != g) ++k;
+        if (k == vals.size()) {
+          if (vals.size() == (size_t)cfmm::kTmaGammaCodes || !(g == g)) ok = false; else vals.push_back(g);
+        }
+        last = g;
+        last_code = (unsigned short)k;
+      }
+      code[(size_t)p] = last_code;
+    }
+    if (ok) {
+      std::vector<double> tab(2 * cfmm::kTmaGammaCodes, 1.0);
+      for (size_t k = 0; k < vals.size(); ++k) {
+        volatile double inv = 1.0 / vals[k];  // IEEE division, as inv of the 32-byte stream (pack_chunks_kernel)
+        tab[k] = inv;
+        tab[cfmm::kTmaGammaCodes + k] = vals[k];
+      }
+      CU_TRY(ctx, s.d_gcode.upload(code));
+      CU_TRY(ctx, s.d_gtab.upload(tab));
+      s.compact_ok = true;
+    }
+  }
   CU_TRY(ctx, s.d_gidx.upload(gidx));
   if (type != CFMM_POOL_UNIV3) {
     std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
@@ -523,12 +570,20 @@ int refresh_scale(cfmm_ctx* ctx, PoolSet& s) {
 
 // the packed stream of the mode this sweep runs in (rebuilt when the mode or the reserves changed)
 template <int POOL>
-int ensure_packed(cfmm_ctx* ctx, PoolSet& s, bool econ, bool fixed, cudaStream_t st) {
-  const int mode = (econ ? 1 : 0) | (fixed ? 2 : 0);
+int ensure_packed(cfmm_ctx* ctx, PoolSet& s, bool econ, bool fixed, bool compact, cudaStream_t st) {
+  const int mode = (econ ? 1 : 0) | (fixed ? 2 : 0) | (compact ? 4 : 0);
   if (s.packed_mode == mode) return CFMM_OK;
-  const size_t bytes = (size_t)s.n_chunks * cfmm::tma_chunk_bytes<POOL>();
-  if (s.d_packed.n != bytes) CU_TRY(ctx, s.d_packed.alloc(bytes));
+  const size_t bytes = (size_t)s.n_chunks * (compact ? cfmm::kTmaChunk * cfmm::kTmaCompactPoolBytes : cfmm::tma_chunk_bytes<POOL>());
+  if (s.d_packed.n < bytes) CU_TRY(ctx, s.d_packed.alloc((size_t)s.n_chunks * cfmm::tma_chunk_bytes<POOL>()));
   const int threads = 256;
+  if (compact) {
+    cfmm::pack_chunks_compact_kernel<<<(unsigned)((s.m_padded + threads - 1) / threads), threads, 0, st>>>(
+        s.d_R.p, s.d_Ai.p, s.d_gcode.p, s.m_padded, s.nb, fixed ? s.d_inv_scale.p : nullptr, s.d_packed.p);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    s.packed_mode = mode;
+    return CFMM_OK;
+  }
   // ProductTwoCoin's economized form streams 1/γ; GeometricMean always γ
   cfmm::pack_chunks_kernel<<<(unsigned)((s.m_padded + threads - 1) / threads), threads, 0, st>>>(
       s.d_R.p, s.d_gam.p, s.d_Ai.p, POOL == 1 ? s.d_w.p : nullptr, s.m_padded,
@@ -539,17 +594,17 @@ int ensure_packed(cfmm_ctx* ctx, PoolSet& s, bool econ, bool fixed, cudaStream_t
   return CFMM_OK;
 }
 
-template <int POOL, bool ECON, bool SKEW, bool FIXED>
+template <int POOL, bool ECON, bool SKEW, bool FIXED, bool COMPACT = false>
 int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, cudaStream_t st) {
-  auto kern = cfmm::product_sweep_tma<POOL, ECON, SKEW, FIXED>;
-  constexpr int kThreads = cfmm::tma_threads<POOL>(), kSmem = cfmm::tma_smem_bytes<POOL>();
+  auto kern = cfmm::product_sweep_tma<POOL, ECON, SKEW, FIXED, COMPACT>;
+  constexpr int kThreads = cfmm::tma_threads<POOL>(), kSmem = cfmm::tma_smem_bytes_c<POOL, COMPACT>();
   int& occ = ctx->occupancy[reinterpret_cast<const void*>(kern)];
   if (occ == 0) {
     CU_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, kSmem));
     if (occ < 1) return fail(ctx, CFMM_ERR_CUDA, "product_sweep_tma does not fit on an SM");
   }
-  int rc = ensure_packed<POOL>(ctx, s, ECON, FIXED, st);
+  int rc = ensure_packed<POOL>(ctx, s, ECON, FIXED, COMPACT, st);
   if (rc != CFMM_OK) return rc;
   // (grid and range table)
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
@@ -557,26 +612,43 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   if (grid > s.n_chunks) grid = (int)s.n_chunks;
   // ---- speed-weighted ranges (see product_tma.cuh) ---------------------------------------
   unsigned* d_dur = nullptr;
-  const bool balancing = ctx->balance && grid <= cfmm::kTmaMaxRanges && s.n_chunks >= (int64_t)grid * 32;
-  if (!balancing) {
-    s.ranges.n = 0;
-  } else {
-    if (!s.h_dur) {
-      CU_TRY(ctx, cudaHostAlloc((void**)&s.h_dur, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned), cudaHostAllocMapped));
-      memset(s.h_dur, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned));
+  const bool tabled = grid <= cfmm::kTmaMaxRanges;
+  const bool balancing = ctx->balance && tabled && s.n_chunks >= (int64_t)grid * 32;
+  auto set_buckets = [&]() {  // b-bucket of every range's first chunk
+    int b = 0;
+    for (int g = 0; g <= grid; ++g) {
+      const int c = g < grid ? s.ranges.first[g] : (int)s.n_chunks - 1;
+      while (b + 1 < s.buckets.n_buckets && s.buckets.first_chunk[b + 1] <= c) ++b;
+      s.ranges.bucket[g] = (short)b;
     }
-    CU_TRY(ctx, cudaHostGetDevicePointer((void**)&d_dur, s.h_dur, 0));
-    if (s.ranges.n != grid) {  // first launch with this grid: even split, neutral speeds
+  };
+  if (!tabled) {
+    s.ranges.n = 0;
+  } else if (s.ranges.n != grid || !balancing) {
+    if (s.ranges.n != grid || s.range_updates != 0) {  // (first launch with this grid, or balancing switched off)
       s.ranges.n = grid;
       for (int g = 0; g <= grid; ++g) s.ranges.first[g] = (int)(s.n_chunks * g / grid);
+      set_buckets();
       s.speed.assign((size_t)grid, 1.0);
       s.range_version = (s.range_version % 250) + 1;
       s.range_updates = 0;
-    } else {
-      // has a launch under the CURRENT table reported from every CTA?  (the words carry the
-      // version of the table they were measured under: launches may still be in flight)
+      s.dur_pending = false;
+    }
+  }
+  if (balancing) {
+    if (!s.h_dur) {
+      CU_TRY(ctx, cudaMallocHost((void**)&s.h_dur, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned)));
+      memset(s.h_dur, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned));
+      CU_TRY(ctx, s.d_dur.alloc(cfmm::kTmaMaxRanges + 1));
+      CU_TRY(ctx, cudaMemset(s.d_dur.p, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned)));
+      CU_TRY(ctx, cudaEventCreateWithFlags(&s.ev_dur, cudaEventDisableTiming));
+    }
+    d_dur = s.d_dur.p;
+    // a copy of the durations has landed: were they all measured under the CURRENT table?
+    if (s.dur_pending && !ctx->capturing && cudaEventQuery(s.ev_dur) == cudaSuccess) {
+      s.dur_pending = false;
       bool complete = true;
-      const volatile unsigned* hd = s.h_dur;
+      const unsigned* hd = s.h_dur;
       for (int g = 0; g < grid && complete; ++g) complete = (hd[g] >> 24) == s.range_version && (hd[g] & 0xffffffu) != 0;
       if (complete) {
         double total = 0.0;
@@ -584,10 +656,21 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
           const double len = (double)(s.ranges.first[g + 1] - s.ranges.first[g]);
           const double dur = (double)(hd[g] & 0xffffffu);
           const double rel = len / dur;  // chunks per tick
-          s.speed[(size_t)g] = s.range_updates == 0 ? rel : 0.5 * s.speed[(size_t)g] + 0.5 * rel;
+          s.speed[(size_t)g] = s.range_updates == 0 ? rel : 0.8 * s.speed[(size_t)g] + 0.2 * rel;
           total += s.speed[(size_t)g];
         }
-        // new boundaries: lengths proportional to speed, at least 2 * warps chunks each, exact total
+        // only the persistent part of the speed differences is worth following (SM position on the
+        // die); launch-to-launch noise is as large: heavy smoothing, and lengths within +-15 % of even
+        {
+          const double mean = total / grid;
+          total = 0.0;
+          for (int g = 0; g < grid; ++g) {
+            double& sp = s.speed[(size_t)g];
+            sp = std::min(1.15 * mean, std::max(0.85 * mean, sp));
+            total += sp;
+          }
+        }
+        // new boundaries: lengths proportional to speed, exact total
         double acc_len = 0.0;
         int prev = 0;
         for (int g = 0; g < grid; ++g) {
@@ -598,12 +681,14 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
           s.ranges.first[g + 1] = end;
           prev = end;
         }
+        set_buckets();
         s.range_version = (s.range_version % 250) + 1;
         s.range_updates++;
       }
     }
   }
   s.ranges.version = s.range_version;
+  s.balancing = balancing;
   s.tma_launches++;
   cfmm::FusedExchange fx = ctx->fx_pending;
   if (fx.mode != 0) {
@@ -613,7 +698,7 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   }
   ProfScope prof(ctx, POOL == 0 ? CFMM_POOL_PRODUCT : CFMM_POOL_GEOMEAN, st);
   const unsigned char* a_packed = s.d_packed.p;
-  const double* a_gam = s.d_gam.p;
+  const double* a_gam = COMPACT ? s.d_gtab.p : s.d_gam.p;  // compact stream: the γ dictionary instead of per-pool γ
   int a_nb = s.nb, a_n = (int)ctx->n_tokens, a_range = s.in_fast_range ? 1 : 0, a_flags = ctx->exact;
   const double* a_scale = FIXED ? s.d_inv_scale.p : nullptr;
   double* a_zero = take_zero_pending(ctx);
@@ -634,6 +719,13 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   CU_TRY(ctx, cudaGetLastError());
   // the grid-barrier target moves only once the launch is known to be accepted
   if (fx.mode != 0) ctx->grid_done_target = fx.target;
+  // fetch the durations now and then: often while the table is still settling, rarely afterwards
+  if (balancing && !ctx->capturing && !s.dur_pending && ++s.since_copy >= (s.range_updates < 8 ? 4 : 256)) {
+    s.since_copy = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(s.h_dur, s.d_dur.p, (size_t)grid * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaEventRecord(s.ev_dur, st));
+    s.dur_pending = true;
+  }
   return CFMM_OK;
 }
 
@@ -641,6 +733,14 @@ template <int POOL>
 int launch_tma(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, cudaStream_t st) {
   const bool econ = ctx->gradient_math != 0;
   const bool fixed = ctx->psi_fixed_point && s.fixed_ok;
+  if constexpr (POOL == 0) {
+    if (econ && ctx->compact_stream && s.compact_ok && !ctx->exact) {
+      if (!s.skewed && fixed) return launch_tma_cfg<0, true, false, true, true>(ctx, s, d_v, d_psi, st);
+      if (!s.skewed && !fixed) return launch_tma_cfg<0, true, false, false, true>(ctx, s, d_v, d_psi, st);
+      if (s.skewed && fixed) return launch_tma_cfg<0, true, true, true, true>(ctx, s, d_v, d_psi, st);
+      return launch_tma_cfg<0, true, true, false, true>(ctx, s, d_v, d_psi, st);
+    }
+  }
 #define CFMM_TMA_CASE(E, K, F) \
   if (econ == E && s.skewed == K && fixed == F) return launch_tma_cfg<POOL, E, K, F>(ctx, s, d_v, d_psi, st);
   CFMM_TMA_CASE(true, false, true)
@@ -1069,7 +1169,7 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
   bool settled = true;
   for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) {
     const PoolSet& ps = ctx->sets[t];
-    if (ps.m > 0 && ps.tma_ok && ctx->use_tma && ctx->balance && (ps.tma_launches == 0 || (ps.ranges.n != 0 && ps.range_updates < 6)))
+    if (ps.m > 0 && ps.tma_ok && ctx->use_tma && ctx->balance && (ps.tma_launches == 0 || (ps.balancing && ps.range_updates < 6)))
       settled = false;
   }
   const bool graphable = ctx->use_graphs && !materialize && contiguous && !ctx->sweep_events &&
@@ -1094,12 +1194,14 @@ int cfmm_sweep(cfmm_ctx* ctx, const double* v, double* psi_out, double* acc_out,
       const int64_t l0 = ctx->launches;
       cudaGraph_t graph = nullptr;
       CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      ctx->capturing = true;
       cudaError_t e = cudaMemcpyAsync(ctx->d_nu.p, v, nb, cudaMemcpyHostToDevice, st);
       const double* res = nullptr;
       if (e == cudaSuccess) rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, false, st, &res);
       if (e == cudaSuccess && rc == CFMM_OK)
         e = cudaMemcpyAsync(psi_out, res, nb + sizeof(double), cudaMemcpyDeviceToHost, st);
       cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+      ctx->capturing = false;
       if (e == cudaSuccess && rc == CFMM_OK && e2 == cudaSuccess && graph &&
           cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
         g->v = v;
@@ -1541,6 +1643,8 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->orient_by_degree = value < 0 ? -1 : (value != 0);
   } else if (!strcmp(key, "psi_fixed_point")) {
     ctx->psi_fixed_point = value != 0;
+  } else if (!strcmp(key, "compact_stream")) {
+    ctx->compact_stream = value != 0;
   } else if (!strcmp(key, "geomean_tma")) {
     ctx->geomean_tma = value != 0;
   } else if (!strcmp(key, "balance")) {

@@ -285,17 +285,19 @@ def test_inrange_math(cr):
     p.close()
 
 
-@pytest.mark.parametrize("variant,fixed,per_sm", [(-1, 1, 0), (0, 1, 0), (0, 0, 0), (0, 1, 1)])
+@pytest.mark.parametrize("variant,fixed,per_sm,compact", [(-1, 1, 0, 1), (0, 1, 0, 1), (0, 0, 0, 1), (0, 1, 1, 1),
+                                                           (0, 1, 0, 0), (0, 0, 0, 0)])
 @pytest.mark.parametrize("m,n", [(200_003, 3_001), (300_000, 20_011), (5_000, 7), (96, 2), (97, 1601), (40_000, 1601)])
-def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, per_sm, m, n):
-    """The b-bucketed TMA kernel with fixed-point and with fp64 slice partials, with two
-    and with one CTA per SM (several buckets at n = 20011, one bucket at n = 7, a single
-    chunk, two buckets with CTAs that straddle the boundary), and the first-generation
-    kernel (-1)."""
+def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, per_sm, compact, m, n):
+    """The b-bucketed TMA kernel with fixed-point and with fp64 slice partials, with the 24-byte
+    (γ dictionary) and the 32-byte stream, with two and with one CTA per SM (several buckets at
+    n = 20011, one bucket at n = 7, a single chunk, two buckets with CTAs that straddle the
+    boundary), and the first-generation kernel (-1)."""
     R, g, Ai = synth.product_pools(m, n, seed=variant + 10)
     p = make_pools(cr, n, product=(R, g, Ai), pre={"tma_variant": variant})
     p.set_option("psi_fixed_point", fixed)
     p.set_option("blocks_per_sm", per_sm)
+    p.set_option("compact_stream", compact)
     for kind in ("near", "wide"):
         v = synth.dual_prices(n, kind)
         Do, Lo = oracle.sweep_product(R, g, Ai, v, threads=8)
@@ -316,6 +318,26 @@ def test_product_gradient_sweep_variants(cr, oracle, synth, variant, fixed, per_
     with pytest.raises(cr.CFMMError):  # the layout is fixed at finalize
         p.set_option("tma_variant", 0)
     p.close()
+
+
+def test_many_fee_levels_keep_the_wide_stream(cr, oracle, synth):
+    """More than 256 distinct fees: no γ dictionary, the 32-byte stream is used; exactly 256 (and a
+    fee of 1.0 among them) still go through the dictionary.  Ψ must match the oracle either way, and
+    the speed feedback of the CTA ranges (many sweeps on the same pools) must not change results."""
+    m, n = 150_000, 2_500
+    R, g, Ai = synth.product_pools(m, n, seed=17)
+    rng = np.random.default_rng(5)
+    for levels in (1000, 256):
+        fees = np.concatenate([[1.0], 1.0 - rng.random(levels - 1) * 0.05])
+        g2 = fees[rng.integers(0, levels, size=m)]
+        g2[:levels] = fees            # every level present
+        p = make_pools(cr, n, product=(R, g2, Ai))
+        for k in range(12):
+            v = synth.dual_prices(n, ["wide", "near"][k % 2], seed=k)
+            Do, Lo = oracle.sweep_product(R, g2, Ai, v, threads=8)
+            psi, acc = p.sweep(v)
+            check_psi(oracle, Ai, Do, Lo, v, n, psi, acc, R=R, g=g2)
+        p.close()
 
 
 def test_fixed_point_slice_rules(cr, oracle, synth):
