@@ -1373,7 +1373,7 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
   if ((rc = commit(0, 0)) != CFMM_OK) return rc;
 
   int age[M];      // history slots, oldest first
-  int cnt = 0, head = 0, iter = 0, status = 2;
+  int cnt = 0, head = 0, iter = 0, status = 2, small_steps = 0;
   while (true) {
     if (!(f == f)) { status = 5; break; }            // NaN objective
     if (pgnorm <= o.pgtol) { status = 0; break; }
@@ -1458,9 +1458,15 @@ int cfmm_solve(cfmm_ctx* ctx, const double* lin, const double* lower, const doub
     ++iter;
     const double f_old = f;
     f = f_new;
+    // L-BFGS-B's factr test -- on two consecutive steps: one short quasi-Newton step (fresh history,
+    // a bound just hit) is not yet evidence of convergence
     if (f_old - f <= o.factr * epsmch * std::max(std::max(std::fabs(f_old), std::fabs(f)), 1.0)) {
-      status = 1;
-      break;
+      if (++small_steps >= 2) {
+        status = 1;
+        break;
+      }
+    } else {
+      small_steps = 0;
     }
   }
   // final ν, and the trades at it (router.jl:106-107)

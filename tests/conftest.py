@@ -63,3 +63,9 @@ def oracle():
 def cr():
     import cfmmrouter_b200
     return cfmmrouter_b200
+
+
+@pytest.fixture(scope="session")
+def synth():
+    from cfmmrouter_b200 import synth as s
+    return s

@@ -18,12 +18,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def synth():
-    from cfmmrouter_b200 import synth as s
-    return s
-
-
 def make_pools(cr, n, product=None, geomean=None, univ3=None, exact=None, pre=None):
     p = cr.DevicePools(n)
     for k, val in (pre or {}).items():  # options that fix the layout (before finalize)
