@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -178,6 +179,7 @@ struct cfmm_ctx {
   unsigned long long state_version = 1;
   int use_graphs = 1;
   bool capturing = false;  // cfmm_sweep is recording a graph: no event queries / side copies
+  bool calibrating = false;  // cfmm_finalize is running its calibration sweeps (range table feedback every launch)
   const void* pinned_ok[2] = {nullptr, nullptr};  // host pointers already verified as pinned
   int balance = 1;              // 1 = TMA kernel: CTA ranges sized by measured CTA speed (feedback), 0 = even split
   int geomean_tma = 1;          // gradient-only GeometricMean sweeps on the TMA kernel (0: first-generation kernel)
@@ -290,7 +292,16 @@ int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
   if (s.m == 0) return CFMM_OK;
   const int64_t m = s.m;
+  const bool timing = getenv("CFMM_TIMING") != nullptr;
+  auto tm0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cfmm]   %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - tm0).count());
+    tm0 = t1;
+  };
   cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m);
+  mark("layout (sorts)");
   const std::vector<int>&oa = lay.oa, &ob = lay.ob;
   s.swapped = lay.swapped;
   s.skewed = lay.skewed;
@@ -334,28 +345,51 @@ int upload_set(cfmm_ctx* ctx, int type) {
       if (s.order[(size_t)p] < 0) ai[(size_t)p] = last; else last = ai[(size_t)p];
     }
   }
+  mark("gather gamma / Ai / gidx");
   CU_TRY(ctx, s.d_gam.upload(gam));
   CU_TRY(ctx, s.d_Ai.upload(ai));
+  mark("upload gamma, Ai");
   s.compact_ok = false;
   if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
     // γ dictionary of the compact stream: fees are categorical in practice
     std::vector<double> vals;
     std::vector<unsigned short> code((size_t)mp, 0);
     bool ok = true;
-    double last = std::nan("");
-    unsigned short last_code = 0;
-    for (int64_t p = 0; p < mp && ok; ++p) {
-      const double g = gam[(size_t)p];
-      if (g != last) {
-        size_t k = 0;
-        while (k < vals.size() && vals[k] != g) ++k;
-        if (k == vals.size()) {
-          if (vals.size() == (size_t)cfmm::kTmaGammaCodes || !(g == g)) ok = false; else vals.push_back(g);
+    {
+      // pass 1 (serial, cheap): the distinct values, through a 1024-slot open-addressing table on the
+      // bit pattern; pass 2 (parallel): the codes
+      constexpr int kSlots = 1024;
+      std::vector<long long> key(kSlots, -1);
+      std::vector<int> val(kSlots, 0);
+      auto slot_of = [&](double g, bool insert) -> int {
+        long long bits;
+        memcpy(&bits, &g, sizeof(bits));
+        if (bits == -1) return -1;  // (a NaN pattern: no dictionary)
+        unsigned h = (unsigned)((unsigned long long)bits * 0x9E3779B97F4A7C15ull >> 54);
+        for (;;) {
+          if (key[h] == bits) return val[h];
+          if (key[h] == -1) {
+            if (!insert || vals.size() == (size_t)cfmm::kTmaGammaCodes) return -1;
+            key[h] = bits;
+            val[h] = (int)vals.size();
+            vals.push_back(g);
+            return val[h];
+          }
+          h = (h + 1) & (kSlots - 1);
         }
-        last = g;
-        last_code = (unsigned short)k;
+      };
+      double last = std::nan("");
+      for (int64_t p = 0; p < mp && ok; ++p) {
+        const double g = gam[(size_t)p];
+        if (g != last) {
+          ok = (g == g) && slot_of(g, true) >= 0;
+          last = g;
+        }
       }
-      code[(size_t)p] = last_code;
+      if (ok) {
+#pragma omp parallel for schedule(static) if (mp > (1 << 16))
+        for (int64_t p = 0; p < mp; ++p) code[(size_t)p] = (unsigned short)slot_of(gam[(size_t)p], false);
+      }
     }
     if (ok) {
       std::vector<double> tab(2 * cfmm::kTmaGammaCodes, 1.0);
@@ -370,6 +404,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
     }
   }
   CU_TRY(ctx, s.d_gidx.upload(gidx));
+  mark("fee dictionary, upload gidx");
   if (type != CFMM_POOL_UNIV3) {
     std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
     int bad_range = 0;
@@ -384,10 +419,13 @@ int upload_set(cfmm_ctx* ctx, int type) {
       bad_range |= ok ? 0 : 1;
     }
     s.in_fast_range = bad_range == 0;
+    mark("gather R");
     CU_TRY(ctx, s.d_R.upload(r));
+    mark("upload R");
     if (s.tma_ok) {
       int rc = refresh_scale(ctx, s);
       if (rc != CFMM_OK) return rc;
+      mark("scale table (device)");
     }
   }
   if (type == CFMM_POOL_GEOMEAN) {
@@ -656,7 +694,8 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
           const double len = (double)(s.ranges.first[g + 1] - s.ranges.first[g]);
           const double dur = (double)(hd[g] & 0xffffffu);
           const double rel = len / dur;  // chunks per tick
-          s.speed[(size_t)g] = s.range_updates == 0 ? rel : 0.8 * s.speed[(size_t)g] + 0.2 * rel;
+          const double keep = ctx->calibrating ? 0.5 : 0.8;
+          s.speed[(size_t)g] = s.range_updates == 0 ? rel : keep * s.speed[(size_t)g] + (1.0 - keep) * rel;
           total += s.speed[(size_t)g];
         }
         // only the persistent part of the speed differences is worth following (SM position on the
@@ -720,7 +759,8 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
   // the grid-barrier target moves only once the launch is known to be accepted
   if (fx.mode != 0) ctx->grid_done_target = fx.target;
   // fetch the durations now and then: often while the table is still settling, rarely afterwards
-  if (balancing && !ctx->capturing && !s.dur_pending && ++s.since_copy >= (s.range_updates < 8 ? 4 : 256)) {
+  if (balancing && !ctx->capturing && !s.dur_pending &&
+      ++s.since_copy >= (ctx->calibrating ? 1 : (s.range_updates < 8 ? 4 : 256))) {
     s.since_copy = 0;
     CU_TRY(ctx, cudaMemcpyAsync(s.h_dur, s.d_dur.p, (size_t)grid * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaEventRecord(s.ev_dur, st));
@@ -1095,11 +1135,43 @@ int cfmm_finalize(cfmm_ctx* ctx) {
   if (!ctx) return CFMM_ERR_INVALID;
   if (ctx->finalized) return fail(ctx, CFMM_ERR_STATE, "already finalized");
   CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const bool timing = getenv("CFMM_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   for (int t = 0; t < 3; ++t) {
     int rc = upload_set(ctx, t);
     if (rc != CFMM_OK) return rc;
+    if (timing) {
+      const auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[cfmm] finalize: pool type %d (%lld pools) %.3f s\n", t, (long long)ctx->sets[t].m,
+              std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    }
   }
   ctx->finalized = true;
+  // Calibration: a dozen gradient sweeps at ν = 1 settle the speed-weighted CTA ranges of the TMA
+  // kernels (and pay the one-time costs of the first launch: function attributes, stream packing)
+  // here rather than in the caller's first sweeps.  ~1 ms.
+  {
+    bool any = false;
+    for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) any = any || (ctx->sets[t].m > 0 && ctx->sets[t].tma_ok);
+    if (any && ctx->balance) {
+      std::vector<double> ones((size_t)ctx->n_tokens, 1.0);
+      CU_TRY(ctx, cudaMemcpy(ctx->d_nu.p, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice));
+      ctx->calibrating = true;
+      int rc = CFMM_OK;
+      for (int it = 0; it < 12 && rc == CFMM_OK; ++it) {
+        const double* view = nullptr;
+        rc = enqueue_sweep(ctx, ctx->d_nu.p, nullptr, false, ctx->stream, &view);
+        if (rc == CFMM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+          rc = fail(ctx, CFMM_ERR_CUDA, "calibration sweep failed: %s", cudaGetErrorString(cudaGetLastError()));
+      }
+      ctx->calibrating = false;
+      if (rc != CFMM_OK) return rc;
+      if (timing)
+        fprintf(stderr, "[cfmm] finalize: calibration %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+  }
   return CFMM_OK;
 }
 
