@@ -71,7 +71,7 @@ struct PoolSet {
   std::vector<int64_t> tick_off;          // univ3: m+1
   std::vector<double> lower, liq;         // univ3: CSR
   // after finalize
-  std::vector<int64_t> order;             // sorted position -> insertion index within type
+  cfmm::HVec<int64_t> order;              // sorted position -> insertion index within type
   std::vector<int64_t> pos_of;            // lazily: insertion index -> sorted position
   DevBuf<double2> d_R, d_w, d_outD, d_outL;
   DevBuf<double> d_gam, d_cp, d_tickdata;
@@ -109,7 +109,7 @@ struct PoolSet {
   unsigned range_version = 1;
   int range_updates = 0;
   int64_t tma_launches = 0;
-  std::vector<uint8_t> swapped; // product: pool stored with its two tokens exchanged (insertion index)
+  cfmm::HVec<uint8_t> swapped;  // product: pool stored with its two tokens exchanged (insertion index)
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
@@ -139,6 +139,10 @@ struct cfmm_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<double> d_nu;  // n
   double* h_stage = nullptr;   // pinned, n+1
+  // finalize uploads: device-order arrays are gathered block by block into two pinned bounce
+  // buffers and copied from there (DMA at link rate, overlapped with the next block's gather)
+  void* h_bounce[2] = {nullptr, nullptr};
+  cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
   int sm_count = 148;
   // options
   int exact = 0;
@@ -276,36 +280,78 @@ inline bool fast_range_ok(double v) { return v >= cfmm::kFastLo && v <= cfmm::kF
 
 // layout of one pool type (pool_layout.hpp): ProductTwoCoin gets the b-bucketed,
 // chunk-padded layout of the TMA kernel; the other types are a-sorted only.
-cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m) {
+cfmm::PoolLayout layout_for(const cfmm_ctx* ctx, int type, const int64_t* Ai, int64_t m,
+                            void (*mark)(const char*) = nullptr) {
   const bool product = type == CFMM_POOL_PRODUCT;
   cfmm::TileShape shape;
   if ((product || type == CFMM_POOL_GEOMEAN) && ctx->tma_variant >= 0) {
     shape.tile = cfmm::kTmaChunk;
     shape.nbmax = cfmm::kTmaNbMax;
   }
-  return cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree, product, shape, shape);
+  return cfmm::build_pool_layout(Ai, m, ctx->n_tokens, ctx->orient_by_degree, product, shape, shape, mark);
 }
 
 int refresh_scale(cfmm_ctx* ctx, PoolSet& s);
+
+// finalize timing (environment CFMM_TIMING): phase marks on stderr
+struct PhaseClock {
+  bool on = getenv("CFMM_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cfmm]   %-36s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+PhaseClock* g_layout_clock = nullptr;  // (finalize is serialised per process while timing is on)
+void layout_mark(const char* what) {
+  if (g_layout_clock) g_layout_clock->mark(what);
+}
+
+constexpr size_t kBounceBytes = (size_t)16 << 20;
+
+// dst[p] = fill(p) for p in [0, count): gathered in parallel into the pinned bounce buffers,
+// block by block, each block copied asynchronously on the context stream while the next one is
+// gathered.  Returns with copies possibly still in flight (upload_set synchronises once).
+template <class T, class Fill>
+cudaError_t upload_streamed(cfmm_ctx* ctx, DevBuf<T>& dst, int64_t count, Fill fill) {
+  cudaError_t e = dst.alloc((size_t)count);
+  if (e != cudaSuccess || count == 0) return e;
+  for (int k = 0; k < 2; ++k) {
+    if (!ctx->h_bounce[k] && (e = cudaMallocHost(&ctx->h_bounce[k], kBounceBytes)) != cudaSuccess) return e;
+    if (!ctx->ev_bounce[k] &&
+        (e = cudaEventCreateWithFlags(&ctx->ev_bounce[k], cudaEventDisableTiming)) != cudaSuccess)
+      return e;
+  }
+  const int64_t per = (int64_t)(kBounceBytes / sizeof(T));
+  int k = 0;
+  for (int64_t lo = 0; lo < count; lo += per, k ^= 1) {
+    const int64_t hi = std::min(count, lo + per);
+    if ((e = cudaEventSynchronize(ctx->ev_bounce[k])) != cudaSuccess) return e;
+    T* out = (T*)ctx->h_bounce[k];
+#pragma omp parallel for schedule(static) if (hi - lo > (1 << 14))
+    for (int64_t p = lo; p < hi; ++p) out[p - lo] = fill(p);
+    if ((e = cudaMemcpyAsync(dst.p + lo, out, (size_t)(hi - lo) * sizeof(T), cudaMemcpyHostToDevice,
+                             ctx->stream)) != cudaSuccess)
+      return e;
+    if ((e = cudaEventRecord(ctx->ev_bounce[k], ctx->stream)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
 
 int upload_set(cfmm_ctx* ctx, int type) {
   PoolSet& s = ctx->sets[type];
   if (s.m == 0) return CFMM_OK;
   const int64_t m = s.m;
-  const bool timing = getenv("CFMM_TIMING") != nullptr;
-  auto tm0 = std::chrono::steady_clock::now();
-  auto mark = [&](const char* what) {
-    if (!timing) return;
-    const auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[cfmm]   %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - tm0).count());
-    tm0 = t1;
-  };
-  cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m);
-  mark("layout (sorts)");
-  const std::vector<int>&oa = lay.oa, &ob = lay.ob;
-  s.swapped = lay.swapped;
+  PhaseClock clock;
+  g_layout_clock = clock.on ? &clock : nullptr;
+  cfmm::PoolLayout lay = layout_for(ctx, type, s.Ai.data(), m, clock.on ? layout_mark : nullptr);
+  g_layout_clock = nullptr;
+  const cfmm::HVec<int>&oa = lay.oa, &ob = lay.ob;
+  s.swapped.swap(lay.swapped);
   s.skewed = lay.skewed;
-  s.order = lay.order;
+  s.order.swap(lay.order);
   s.m_padded = lay.m_padded;
   s.tma_ok = lay.bucketed;
   s.nb = (int)lay.nb;
@@ -325,70 +371,60 @@ int upload_set(cfmm_ctx* ctx, int type) {
     }
   }
   const int64_t mp = s.m_padded;
-  std::vector<double> gam((size_t)mp, 1.0);
-  std::vector<int2> ai((size_t)mp);
-  std::vector<int64_t> gidx((size_t)mp, -1);
-#pragma omp parallel for schedule(static) if (mp > (1 << 16))
-  for (int64_t p = 0; p < mp; ++p) {
-    const int64_t i = s.order[(size_t)p];
-    if (i < 0) continue;
-    gam[(size_t)p] = s.gamma[(size_t)i];
-    ai[(size_t)p] = make_int2(oa[(size_t)i], ob[(size_t)i]);
-    // bit 62 of the global index marks a pool stored with its tokens exchanged
-    gidx[(size_t)p] = s.gidx[(size_t)i] | (s.swapped[(size_t)i] ? (1ll << 62) : 0);
-  }
-  {
-    // padding: keyed like the previous real pool of the bucket (monotone a); pads trail
-    // their bucket, so a serial pass that only touches pads fixes them up
-    int2 last = make_int2(0, 1);
-    for (int64_t p = 0; p < mp; ++p) {
-      if (s.order[(size_t)p] < 0) ai[(size_t)p] = last; else last = ai[(size_t)p];
-    }
-  }
-  mark("gather gamma / Ai / gidx");
-  CU_TRY(ctx, s.d_gam.upload(gam));
-  CU_TRY(ctx, s.d_Ai.upload(ai));
-  mark("upload gamma, Ai");
+  const int64_t* order = s.order.data();
+  // padding pools trail their bucket (fewer than one chunk of them): keyed like the last real
+  // pool before them (monotone a), zero reserves, unit fee
+  const auto real_before = [order](int64_t p) -> int64_t {
+    while (p >= 0 && order[p] < 0) --p;
+    return p < 0 ? -1 : order[p];
+  };
+  CU_TRY(ctx, upload_streamed(ctx, s.d_gam, mp, [&](int64_t p) {
+    const int64_t i = order[p];
+    return i < 0 ? 1.0 : s.gamma[(size_t)i];
+  }));
+  CU_TRY(ctx, upload_streamed(ctx, s.d_Ai, mp, [&](int64_t p) {
+    const int64_t i = real_before(p);
+    return i < 0 ? make_int2(0, 1) : make_int2(oa[(size_t)i], ob[(size_t)i]);
+  }));
+  // bit 62 of the global index marks a pool stored with its tokens exchanged
+  CU_TRY(ctx, upload_streamed(ctx, s.d_gidx, mp, [&](int64_t p) {
+    const int64_t i = order[p];
+    return i < 0 ? (int64_t)-1 : (s.gidx[(size_t)i] | (s.swapped[(size_t)i] ? (1ll << 62) : 0));
+  }));
+  clock.mark("gather + upload gamma, Ai, gidx");
   s.compact_ok = false;
   if (type == CFMM_POOL_PRODUCT && s.tma_ok) {
-    // γ dictionary of the compact stream: fees are categorical in practice
+    // γ dictionary of the compact stream: fees are categorical in practice.  Pass 1 (serial,
+    // cheap): the distinct values, through a 1024-slot open-addressing table on the bit pattern;
+    // pass 2 (the upload's gather): the codes
     std::vector<double> vals;
-    std::vector<unsigned short> code((size_t)mp, 0);
-    bool ok = true;
-    {
-      // pass 1 (serial, cheap): the distinct values, through a 1024-slot open-addressing table on the
-      // bit pattern; pass 2 (parallel): the codes
-      constexpr int kSlots = 1024;
-      std::vector<long long> key(kSlots, -1);
-      std::vector<int> val(kSlots, 0);
-      auto slot_of = [&](double g, bool insert) -> int {
-        long long bits;
-        memcpy(&bits, &g, sizeof(bits));
-        if (bits == -1) return -1;  // (a NaN pattern: no dictionary)
-        unsigned h = (unsigned)((unsigned long long)bits * 0x9E3779B97F4A7C15ull >> 54);
-        for (;;) {
-          if (key[h] == bits) return val[h];
-          if (key[h] == -1) {
-            if (!insert || vals.size() == (size_t)cfmm::kTmaGammaCodes) return -1;
-            key[h] = bits;
-            val[h] = (int)vals.size();
-            vals.push_back(g);
-            return val[h];
-          }
-          h = (h + 1) & (kSlots - 1);
+    constexpr int kSlots = 1024;
+    std::vector<long long> key(kSlots, -1);
+    std::vector<int> val(kSlots, 0);
+    auto slot_of = [&](double g, bool insert) -> int {
+      long long bits;
+      memcpy(&bits, &g, sizeof(bits));
+      if (bits == -1) return -1;  // (a NaN pattern: no dictionary)
+      unsigned h = (unsigned)((unsigned long long)bits * 0x9E3779B97F4A7C15ull >> 54);
+      for (;;) {
+        if (key[h] == bits) return val[h];
+        if (key[h] == -1) {
+          if (!insert || vals.size() == (size_t)cfmm::kTmaGammaCodes) return -1;
+          key[h] = bits;
+          val[h] = (int)vals.size();
+          vals.push_back(g);
+          return val[h];
         }
-      };
-      double last = std::nan("");
-      for (int64_t p = 0; p < mp && ok; ++p) {
-        const double g = gam[(size_t)p];
-        if (g != last) {
-          ok = (g == g) && slot_of(g, true) >= 0;
-          last = g;
-        }
+        h = (h + 1) & (kSlots - 1);
       }
-      if (ok) {
-#pragma omp parallel for schedule(static) if (mp > (1 << 16))
-        for (int64_t p = 0; p < mp; ++p) code[(size_t)p] = (unsigned short)slot_of(gam[(size_t)p], false);
+    };
+    bool ok = slot_of(1.0, true) >= 0;  // (the padding pools' fee)
+    double last = 1.0;
+    for (int64_t i = 0; i < m && ok; ++i) {
+      const double g = s.gamma[(size_t)i];
+      if (g != last) {
+        ok = (g == g) && slot_of(g, true) >= 0;
+        last = g;
       }
     }
     if (ok) {
@@ -398,44 +434,42 @@ int upload_set(cfmm_ctx* ctx, int type) {
         tab[k] = inv;
         tab[cfmm::kTmaGammaCodes + k] = vals[k];
       }
-      CU_TRY(ctx, s.d_gcode.upload(code));
+      CU_TRY(ctx, upload_streamed(ctx, s.d_gcode, mp, [&](int64_t p) {
+        const int64_t i = order[p];
+        return (unsigned short)slot_of(i < 0 ? 1.0 : s.gamma[(size_t)i], false);
+      }));
       CU_TRY(ctx, s.d_gtab.upload(tab));
       s.compact_ok = true;
     }
+    clock.mark("fee dictionary + codes");
   }
-  CU_TRY(ctx, s.d_gidx.upload(gidx));
-  mark("fee dictionary, upload gidx");
   if (type != CFMM_POOL_UNIV3) {
-    std::vector<double2> r((size_t)mp, make_double2(0.0, 0.0));
     int bad_range = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad_range) if (mp > (1 << 16))
-    for (int64_t p = 0; p < mp; ++p) {
-      const int64_t i = s.order[(size_t)p];
-      if (i < 0) continue;
-      r[(size_t)p] = s.swapped[(size_t)i] ? make_double2(s.R[2 * i + 1], s.R[2 * i])
-                                          : make_double2(s.R[2 * i], s.R[2 * i + 1]);
+#pragma omp parallel for schedule(static) reduction(| : bad_range) if (m > (1 << 16))
+    for (int64_t i = 0; i < m; ++i) {
       const bool ok = fast_range_ok(s.R[2 * i]) && fast_range_ok(s.R[2 * i + 1]) &&
                       fast_range_ok(s.gamma[(size_t)i]) && s.gamma[(size_t)i] <= 1.0;
       bad_range |= ok ? 0 : 1;
     }
     s.in_fast_range = bad_range == 0;
-    mark("gather R");
-    CU_TRY(ctx, s.d_R.upload(r));
-    mark("upload R");
+    CU_TRY(ctx, upload_streamed(ctx, s.d_R, mp, [&](int64_t p) {
+      const int64_t i = order[p];
+      if (i < 0) return make_double2(0.0, 0.0);
+      return s.swapped[(size_t)i] ? make_double2(s.R[2 * i + 1], s.R[2 * i])
+                                  : make_double2(s.R[2 * i], s.R[2 * i + 1]);
+    }));
+    clock.mark("range check, gather + upload R");
     if (s.tma_ok) {
       int rc = refresh_scale(ctx, s);
       if (rc != CFMM_OK) return rc;
-      mark("scale table (device)");
+      clock.mark("scale table (device)");
     }
   }
   if (type == CFMM_POOL_GEOMEAN) {
-    std::vector<double2> w((size_t)mp, make_double2(0.5, 0.5));  // (padding pools: any valid weights)
-#pragma omp parallel for schedule(static) if (mp > (1 << 16))
-    for (int64_t p = 0; p < mp; ++p) {
-      const int64_t i = s.order[(size_t)p];
-      if (i >= 0) w[(size_t)p] = make_double2(s.w[2 * i], s.w[2 * i + 1]);
-    }
-    CU_TRY(ctx, s.d_w.upload(w));
+    CU_TRY(ctx, upload_streamed(ctx, s.d_w, mp, [&](int64_t p) {
+      const int64_t i = order[p];  // (padding pools: any valid weights)
+      return i < 0 ? make_double2(0.5, 0.5) : make_double2(s.w[2 * i], s.w[2 * i + 1]);
+    }));
   }
   if (type == CFMM_POOL_UNIV3) {
     // compute_at_tick (src/cfmms.jl:294-313) for every tick, once, on the host:
@@ -480,6 +514,8 @@ int upload_set(cfmm_ctx* ctx, int type) {
     CU_TRY(ctx, s.d_tick.upload(tick));
     CU_TRY(ctx, s.d_tickdata.upload(td));
   }
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the bounce copies read the staging below
+  clock.mark("other arrays, drain");
   // host staging is no longer needed (order is kept for update_reserves)
   std::vector<double>().swap(s.R);
   std::vector<double>().swap(s.gamma);
@@ -490,6 +526,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
   std::vector<int64_t>().swap(s.tick_off);
   std::vector<double>().swap(s.lower);
   std::vector<double>().swap(s.liq);
+  clock.mark("free host staging");
   return CFMM_OK;
 }
 
@@ -977,6 +1014,10 @@ void cfmm_destroy(cfmm_ctx* ctx) {
   ctx->d_accum[0].release();
   ctx->d_accum[1].release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  for (void* b : ctx->h_bounce)
+    if (b) cudaFreeHost(b);
+  for (cudaEvent_t e : ctx->ev_bounce)
+    if (e) cudaEventDestroy(e);
   if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

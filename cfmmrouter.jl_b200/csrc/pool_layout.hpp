@@ -9,6 +9,8 @@
 //    whole tiles (padding = position with order -1), one bucket id per tile.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -16,22 +18,49 @@
 
 namespace cfmm {
 
-// Stable counting sort of the items 0..m-1 by key(item) in [0, K), over `src` (the current
-// order; null = identity): out[pos] = item.  Parallel form: every thread counts and then
-// scatters its own contiguous block, with per-(key, thread) offsets -- stable, no atomics.
-template <class KeyFn>
-inline void counting_sort_stable(const int64_t* src, int64_t m, int64_t K, KeyFn key,
-                                 std::vector<int64_t>& out) {
-  out.assign((size_t)m, 0);
-  int T = 1;
+// Host vectors of the layout: default-initialised on resize (no serial zero-fill -- and no serial
+// page-fault pass -- over arrays every element of which a parallel loop is about to write).
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  using std::allocator<T>::allocator;
+  template <class U>
+  void construct(U* p) noexcept {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+};
+template <class T>
+using HVec = std::vector<T, DefaultInitAlloc<T>>;
+
+inline int layout_threads(int64_t m) {
 #ifdef _OPENMP
-  T = omp_get_max_threads();
-  const int64_t cap = (int64_t)32 << 20;  // counters in flight
-  if ((int64_t)T * K > cap) T = (int)(cap / (K > 0 ? K : 1));
-  if (T < 1) T = 1;
-  if (m < (1 << 16)) T = 1;
+  return m < (1 << 16) ? 1 : omp_get_max_threads();
+#else
+  (void)m;
+  return 1;
 #endif
-  std::vector<int64_t> cnt((size_t)T * (size_t)K, 0);
+}
+
+// Stable counting sort of `m` items by key(item) in [0, K): out[pos] = item, items taken from `src`
+// (the current order; null = identity).  Every thread counts and then scatters its own contiguous
+// block with per-(thread, key) offsets -- stable, no atomics; the offsets come from a key-blocked
+// parallel scan (thread-major counters, so each block is read row by row).  `totals` (optional):
+// the K key counts.
+template <class KeyFn>
+inline void counting_sort_stable(const int64_t* src, int64_t m, int64_t K, KeyFn key, int64_t* out,
+                                 std::vector<int64_t>* totals = nullptr) {
+  int T = layout_threads(m);
+  // the counters must stay small next to the items: each thread sweeps K of them twice
+  while (T > 1 && (int64_t)T * K > 4 * m) T /= 2;
+  HVec<int64_t> cnt((size_t)T * (size_t)K);
+  std::vector<int64_t> base((size_t)K + 1, 0);
 #pragma omp parallel num_threads(T)
   {
 #ifdef _OPENMP
@@ -41,24 +70,52 @@ inline void counting_sort_stable(const int64_t* src, int64_t m, int64_t K, KeyFn
 #endif
     const int64_t lo = m * t / T, hi = m * (t + 1) / T;
     int64_t* c = cnt.data() + (size_t)t * (size_t)K;
+    for (int64_t k = 0; k < K; ++k) c[k] = 0;
     for (int64_t p = lo; p < hi; ++p) c[key(src ? src[p] : p)]++;
+#pragma omp barrier
+    const int64_t k0 = K * t / T, k1 = K * (t + 1) / T;  // this thread's block of keys
+    for (int64_t k = k0; k < k1; ++k) base[(size_t)k + 1] = 0;
+    for (int tt = 0; tt < T; ++tt) {
+      const int64_t* row = cnt.data() + (size_t)tt * (size_t)K;
+      for (int64_t k = k0; k < k1; ++k) base[(size_t)k + 1] += row[k];
+    }
 #pragma omp barrier
 #pragma omp single
     {
-      int64_t run = 0;  // offsets in (key, thread) order
-      for (int64_t k = 0; k < K; ++k)
-        for (int tt = 0; tt < T; ++tt) {
-          int64_t& x = cnt[(size_t)tt * (size_t)K + (size_t)k];
-          const int64_t v = x;
-          x = run;
-          run += v;
-        }
+      for (int64_t k = 0; k < K; ++k) base[(size_t)k + 1] += base[(size_t)k];  // exclusive starts
     }
+    // (implicit barrier) offsets in (key, thread) order, key block by key block
+    {
+      std::vector<int64_t> run(base.begin() + k0, base.begin() + k1);
+      for (int tt = 0; tt < T; ++tt) {
+        int64_t* row = cnt.data() + (size_t)tt * (size_t)K;
+        for (int64_t k = k0; k < k1; ++k) {
+          const int64_t v = row[k];
+          row[k] = run[(size_t)(k - k0)];
+          run[(size_t)(k - k0)] += v;
+        }
+      }
+    }
+#pragma omp barrier
     for (int64_t p = lo; p < hi; ++p) {
       const int64_t item = src ? src[p] : p;
-      out[(size_t)c[key(item)]++] = item;
+      out[c[key(item)]++] = item;
     }
   }
+  if (totals) {
+    totals->resize((size_t)K);
+    for (int64_t k = 0; k < K; ++k) (*totals)[(size_t)k] = base[(size_t)k + 1] - base[(size_t)k];
+  }
+}
+
+// Serial form over a small block (one b-bucket): counters are 32-bit and caller-provided.
+template <class KeyFn>
+inline void counting_sort_block(const int64_t* src, int64_t m, int64_t K, KeyFn key, int64_t* out,
+                                std::vector<int32_t>& cnt) {
+  cnt.assign((size_t)K + 1, 0);
+  for (int64_t p = 0; p < m; ++p) cnt[(size_t)key(src[p]) + 1]++;
+  for (int64_t k = 0; k < K; ++k) cnt[(size_t)k + 1] += cnt[(size_t)k];
+  for (int64_t p = 0; p < m; ++p) out[cnt[(size_t)key(src[p])]++] = src[p];
 }
 
 struct TileShape {
@@ -68,9 +125,9 @@ struct TileShape {
 };
 
 struct PoolLayout {
-  std::vector<int64_t> order;    // device position -> insertion index within the type, -1 = padding
-  std::vector<int> oa, ob;       // device orientation per insertion index (0-based tokens)
-  std::vector<uint8_t> swapped;  // per insertion index: stored with its two tokens exchanged
+  HVec<int64_t> order;           // device position -> insertion index within the type, -1 = padding
+  HVec<int> oa, ob;              // device orientation per insertion index (0-based tokens)
+  HVec<uint8_t> swapped;         // per insertion index: stored with its two tokens exchanged
   std::vector<int> tile_bucket;  // bucket of every chunk (bucketed layouts only)
   int64_t m_padded = 0;
   int64_t nb = 0;                // bucket width in tokens
@@ -79,26 +136,50 @@ struct PoolLayout {
   bool used_skew_shape = false;
 };
 
+// Token degrees (pools per token), by per-thread histograms merged key block by key block: no
+// atomics, so a hub token costs what any other token does.
+inline std::vector<int64_t> token_degrees(const int64_t* Ai, int64_t m, int64_t n_tokens) {
+  int T = layout_threads(m);
+  while (T > 1 && (int64_t)T * n_tokens > 4 * m) T /= 2;
+  HVec<int32_t> part((size_t)T * (size_t)n_tokens);
+  std::vector<int64_t> deg((size_t)n_tokens, 0);
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num();
+#else
+    const int t = 0;
+#endif
+    int32_t* c = part.data() + (size_t)t * (size_t)n_tokens;
+    for (int64_t k = 0; k < n_tokens; ++k) c[k] = 0;
+    for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i) {
+      c[Ai[2 * i] - 1]++;
+      c[Ai[2 * i + 1] - 1]++;
+    }
+#pragma omp barrier
+    for (int tt = 0; tt < T; ++tt) {
+      const int32_t* row = part.data() + (size_t)tt * (size_t)n_tokens;
+      for (int64_t k = n_tokens * t / T; k < n_tokens * (t + 1) / T; ++k) deg[(size_t)k] += row[k];
+    }
+  }
+  return deg;
+}
+
 // Ai: [2m] 1-based token ids (validated by the caller).  orient: -1 auto (orient
 // only when hubs are detected), 0 never, 1 always; only honoured when `symmetric`
 // (ProductTwoCoin).  `normal` / `skew`: tile shapes for uniform / hub-detected graphs.
+// `mark` (optional): called after each phase with its name (finalize timing).
 inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_tokens, int orient,
-                                    bool symmetric, TileShape normal, TileShape skew) {
+                                    bool symmetric, TileShape normal, TileShape skew,
+                                    void (*mark)(const char*) = nullptr) {
   PoolLayout lay;
   lay.oa.resize((size_t)m);
   lay.ob.resize((size_t)m);
-  lay.swapped.assign((size_t)m, 0);
+  lay.swapped.resize((size_t)m);
   lay.m_padded = m;
   std::vector<int64_t> deg;
   if (symmetric && orient != 0) {
-    deg.assign((size_t)n_tokens, 0);
-#pragma omp parallel for schedule(static) if (m > (1 << 16))
-    for (int64_t i = 0; i < m; ++i) {
-#pragma omp atomic
-      deg[(size_t)Ai[2 * i] - 1]++;
-#pragma omp atomic
-      deg[(size_t)Ai[2 * i + 1] - 1]++;
-    }
+    deg = token_degrees(Ai, m, n_tokens);
     // hub detection: some token sits in far more pools than the average token.
     // On uniform graphs orientation only perturbs the layout (measured -2.6 %),
     // so in auto mode it is applied to skewed graphs only.
@@ -116,12 +197,21 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     lay.oa[(size_t)i] = sw ? b : a;
     lay.ob[(size_t)i] = sw ? a : b;
   }
-  // stable counting sort by the first token
-  counting_sort_stable(nullptr, m, n_tokens, [&](int64_t i) { return (int64_t)lay.oa[(size_t)i]; }, lay.order);
+  if (mark) mark("layout: degrees, orientation");
   lay.used_skew_shape = lay.skewed && skew.tile > 0;
   const TileShape shape = lay.used_skew_shape ? skew : normal;
-  if (shape.tile <= 0 || m == 0) return lay;
-  // b-bucketed order: (bucket(b), a), each bucket padded to whole tiles
+  const auto by_a = [&](int64_t i) { return (int64_t)lay.oa[(size_t)i]; };
+  const auto sort_by_a_only = [&]() {
+    lay.order.resize((size_t)m);
+    counting_sort_stable(nullptr, m, n_tokens, by_a, lay.order.data());
+    if (mark) mark("layout: sort by first token");
+  };
+  if (shape.tile <= 0 || m == 0) {
+    sort_by_a_only();
+    return lay;
+  }
+  // b-bucketed order (bucket(b), a, insertion index), each bucket padded to whole tiles: group
+  // by bucket first (few keys), then sort every bucket by a on its own
   const int64_t tile = shape.tile;
   const int64_t B = (n_tokens + shape.nbmax - 1) / shape.nbmax;
   int64_t nb = (n_tokens + B - 1) / B;
@@ -129,39 +219,42 @@ inline PoolLayout build_pool_layout(const int64_t* Ai, int64_t m, int64_t n_toke
     const int64_t up = (nb + shape.nb_align - 1) / shape.nb_align * shape.nb_align;
     if (up <= shape.nbmax) nb = up;
   }
-  std::vector<int64_t> cnt((size_t)B + 1, 0);
-  std::vector<int64_t> grouped;  // the a-sorted order, stably regrouped by bucket(b)
-  counting_sort_stable(lay.order.data(), m, B, [&](int64_t i) { return (int64_t)(lay.ob[(size_t)i] / nb); },
-                       grouped);
-  {
-    // bucket sizes from the grouped order: bucket ids are non-decreasing along it
-    std::vector<int64_t> c2((size_t)B, 0);
-#pragma omp parallel for schedule(static) if (m > (1 << 16))
-    for (int64_t i = 0; i < m; ++i) {
-#pragma omp atomic
-      c2[(size_t)(lay.ob[(size_t)i] / nb)]++;
-    }
-    for (int64_t k = 0; k < B; ++k) cnt[(size_t)k + 1] = c2[(size_t)k];
+  HVec<int64_t> grouped((size_t)m);
+  std::vector<int64_t> cnt;
+  counting_sort_stable(nullptr, m, B, [&](int64_t i) { return (int64_t)(lay.ob[(size_t)i] / nb); },
+                       grouped.data(), &cnt);
+  if (mark) mark("layout: group by bucket");
+  std::vector<int64_t> start((size_t)B + 1, 0), first((size_t)B + 1, 0);  // padded / unpadded starts
+  for (int64_t k = 0; k < B; ++k) {
+    start[(size_t)k + 1] = start[(size_t)k] + (cnt[(size_t)k] + tile - 1) / tile * tile;
+    first[(size_t)k + 1] = first[(size_t)k] + cnt[(size_t)k];
   }
-  int64_t padded = 0;
-  for (int64_t k = 0; k < B; ++k) padded += (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
-  if (padded > 2 * m + 8 * tile) return lay;  // too sparse per bucket: a-sorted layout only
-  std::vector<int64_t> start((size_t)B + 1, 0);  // padded start of each bucket
-  for (int64_t k = 0; k < B; ++k)
-    start[(size_t)k + 1] = start[(size_t)k] + (cnt[(size_t)k + 1] + tile - 1) / tile * tile;
-  std::vector<int64_t> order((size_t)padded, -1);
-  {
-    // grouped[] is the padded order minus the pads: bucket k's pools go to start[k] onwards
-    std::vector<int64_t> first((size_t)B + 1, 0);  // unpadded start of each bucket
-    for (int64_t k = 0; k < B; ++k) first[(size_t)k + 1] = first[(size_t)k] + cnt[(size_t)k + 1];
-#pragma omp parallel for schedule(static) if (m > (1 << 16))
-    for (int64_t q = 0; q < m; ++q) {
-      const int64_t i = grouped[(size_t)q];
-      const int64_t k = lay.ob[(size_t)i] / nb;
-      order[(size_t)(start[(size_t)k] + (q - first[(size_t)k]))] = i;
+  const int64_t padded = start[(size_t)B];
+  if (padded > 2 * m + 8 * tile) {  // too sparse per bucket: a-sorted layout only
+    sort_by_a_only();
+    return lay;
+  }
+  lay.order.resize((size_t)padded);
+  const int T = layout_threads(m);
+  if (B >= 4 || T == 1) {
+#pragma omp parallel num_threads(T)
+    {
+      std::vector<int32_t> c;
+#pragma omp for schedule(dynamic, 1)
+      for (int64_t k = 0; k < B; ++k) {
+        int64_t* out = lay.order.data() + start[(size_t)k];
+        counting_sort_block(grouped.data() + first[(size_t)k], cnt[(size_t)k], n_tokens, by_a, out, c);
+        for (int64_t q = cnt[(size_t)k]; q < start[(size_t)k + 1] - start[(size_t)k]; ++q) out[q] = -1;
+      }
+    }
+  } else {
+    for (int64_t k = 0; k < B; ++k) {
+      int64_t* out = lay.order.data() + start[(size_t)k];
+      counting_sort_stable(grouped.data() + first[(size_t)k], cnt[(size_t)k], n_tokens, by_a, out);
+      for (int64_t q = cnt[(size_t)k]; q < start[(size_t)k + 1] - start[(size_t)k]; ++q) out[q] = -1;
     }
   }
-  lay.order.swap(order);
+  if (mark) mark("layout: sort buckets by first token");
   lay.m_padded = padded;
   lay.nb = nb;
   lay.bucketed = true;
