@@ -712,7 +712,11 @@ _REAL_STDOUT = None
 def emit(line: dict):
     """The ONE JSON line, on the real stdout (libraries such as NCCL print
     banners to fd 1; everything else this process writes goes to stderr)."""
-    data = (json.dumps(line) + "\n").encode()
+    def plain(o):  # numpy scalars that reach the line through the parity / phase objects
+        if isinstance(o, np.generic):
+            return o.item()
+        raise TypeError(f"not JSON serialisable: {type(o).__name__}")
+    data = (json.dumps(line, default=plain) + "\n").encode()
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 

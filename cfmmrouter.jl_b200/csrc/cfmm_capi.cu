@@ -161,7 +161,7 @@ struct cfmm_ctx {
   DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
-  int coop_launch = 1;            // fused exchange: launch the sweep kernel cooperatively (co-residency guaranteed)
+  int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured: +8 us back to back, +330 us after an event or copy)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived

@@ -211,9 +211,14 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *   "blocks_per_sm"    resident CTAs per SM of the persistent kernels (measurement knob).
  *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
  *                      in the sweep kernel's tail; 0 = separate exchange launch.
- *   "coop_launch"      multi-GPU: 1 (default) = the fused sweep+exchange kernel is launched with
- *                      cudaLaunchCooperativeKernel (its grid barrier needs every CTA resident);
- *                      0 = plain launch (residency inferred from the occupancy query).
+ *   "coop_launch"      multi-GPU: 1 = the fused sweep+exchange kernel is launched with
+ *                      cudaLaunchCooperativeKernel (the driver guarantees that every CTA of its
+ *                      grid barrier is resident, or fails the launch); 0 (default) = plain launch,
+ *                      residency follows from the occupancy query that sizes the persistent grid,
+ *                      and a barrier that cannot complete ends in CFMM_ERR_COMM after the poll
+ *                      bound instead of hanging.  Measured at N = 2 on B200: the cooperative
+ *                      launch costs +8 us per step back to back and +330 us whenever an event
+ *                      record or a copy precedes it on the stream.
  *   "exchange_bypass"  multi-GPU: 1 = sweeps skip the exchange and return this rank's partial
  *                      [psi ; acc] (verification; every rank must set it alike).
  *   "exchange_two_shot" multi-GPU: force the one-shot (0) / two-shot (1) LL protocol

@@ -144,6 +144,9 @@ def _worker(rank, world, port, out_dir):
         q.set_option("fused_exchange", 1)
         q.set_option("exchange_two_shot", 1 if world == 2 else 0)
         fres += [q.sweep(vq) for _ in range(2)]
+        q.set_option("coop_launch", 1)  # the same fused kernel under cudaLaunchCooperativeKernel
+        fres += [q.sweep(vq) for _ in range(2)]
+        q.set_option("coop_launch", 0)
         np.savez(os.path.join(out_dir, f"fused{rank}.npz"), psi=np.stack([r[0] for r in fres]),
                  acc=np.array([r[1] for r in fres]), launches=fused_launches)
         q.close()

@@ -12,7 +12,7 @@ run() { # name, extra args
 }
 run bench --steps 500 --warmup 20
 run bench_k20 --steps 20 --warmup 3 --strong 0 --verify 0
-run bench_nocoop --steps 500 --warmup 20 --strong 0 --verify 0 --opt coop_launch=0
+run bench_coop --steps 200 --warmup 20 --strong 0 --verify 0 --opt coop_launch=1
 run bench_nccl --steps 300 --warmup 10 --strong 0 --verify 0 --exchange nccl
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/${tag}_n${N}_reference.json 2>> gpurun_out/${tag}_n${N}_bench.err
 cat gpurun_out/${tag}_n${N}_reference.json
