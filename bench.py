@@ -362,6 +362,7 @@ def run_ours(args):
             if sampler_ref[0] is not None:
                 sampler_ref[0]._sample_once()
             barrier()
+            pools.comm_check()
             return float(sum(a.elapsed_time(b) for a, b in ev))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -371,6 +372,7 @@ def run_ours(args):
         if sampler_ref[0] is not None:
             sampler_ref[0]._sample_once()  # GPU still busy with the queued steps
         barrier()
+        pools.comm_check()  # a timed-out exchange must fail the run, not slow it
         return e0.elapsed_time(e1)
 
     extra = {}
@@ -387,8 +389,13 @@ def run_ours(args):
         launches = pools.launch_count - l0
         # a driver-sized K can be a millisecond of GPU time: also a region of >= 50 ms of the
         # same steps (`sustained`), so that the clocks are sampled under load
-        if ms_total < 50.0 and not flushed:
-            k2 = int(min(50_000, max(args.steps, np.ceil(60.0 * args.steps / max(ms_total, 1e-3)))))
+        ms_dec = ms_total
+        if world > 1:  # every rank must take the same branch and launch the same number of sweeps
+            t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_dec = t.item()
+        if ms_dec < 50.0 and not flushed:
+            k2 = int(min(50_000, max(args.steps, np.ceil(60.0 * args.steps / max(ms_dec, 1e-3)))))
             ms2 = timed_region(k2)
             extra["sustained"] = {"steps": k2, "ms_per_step": ms2 / k2}
         sampler.stop()
@@ -624,6 +631,7 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
+    phases = phase_trace(ps, fn, barrier, rank)  # per-phase timeline of the strong step on rank 0
     # single GPU, same 10M pools: every rank sweeps its weak shard without the exchange; rank 0's is seed 1234
     pools_weak.set_option("exchange_bypass", 1)
     fn1 = make_step(pools_weak)
@@ -639,6 +647,7 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
     return {"pools_total": m, "pools_per_gpu": hi - lo, "steps": steps, "us_per_step": 1e3 * ms / steps,
             "value": m * steps / (ms * 1e-3), "unit": UNIT,
             "single_gpu_us_per_step": 1e3 * ms1 / steps, "speedup_vs_single_gpu": ms1 / ms,
+            "phases_rank0_us": phases,
             "note": "same total pools split over the ranks (BASELINE configs[4] as written); single_gpu = "
                     "rank 0 sweeping all of them alone, in the same run"}
 

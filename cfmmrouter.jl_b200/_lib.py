@@ -74,6 +74,7 @@ SYMBOLS = {
     "cfmm_comm_export": (C.c_int, [_ctx, C.c_void_p]),
     "cfmm_comm_attach": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
     "cfmm_comm_detach": (C.c_int, [_ctx]),
+    "cfmm_comm_check": (C.c_int, [_ctx]),
 }
 
 _lib = None

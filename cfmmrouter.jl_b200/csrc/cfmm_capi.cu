@@ -1963,6 +1963,18 @@ int cfmm_comm_attach(cfmm_ctx* ctx, int world, int rank, const void* handles) {
   return CFMM_OK;
 }
 
+// For callers of the asynchronous entry points (cfmm_sweep_device*): did any exchange enqueued so
+// far give up on a peer?  Synchronises the context's last stream first.
+int cfmm_comm_check(cfmm_ctx* ctx) {
+  if (!ctx) return CFMM_ERR_INVALID;
+  if (!ctx->comm.attached()) return CFMM_OK;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->last_stream ? ctx->last_stream : ctx->stream));
+  if (ctx->comm.timed_out())
+    return fail(ctx, CFMM_ERR_COMM, "peer exchange timed out: a rank of the group did not deliver its packets");
+  return CFMM_OK;
+}
+
 int cfmm_comm_detach(cfmm_ctx* ctx) {
   if (!ctx) return CFMM_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -78,10 +78,13 @@ __device__ __forceinline__ ulonglong2 ld_packet(const ulonglong2* p) {
 }
 
 // poll one packet until both words carry `tag`; false (and the error word raised) on timeout
+__device__ __forceinline__ bool packet_ready(const ulonglong2& v, unsigned long long tag) {
+  return (v.x & 0xffffffffull) == tag && (v.y & 0xffffffffull) == tag;
+}
 __device__ __forceinline__ bool poll_packet(const ExchangeView& x, const ulonglong2* q, unsigned long long tag,
                                             ulonglong2* out) {
   ulonglong2 v = ld_packet(q);
-  if ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag) {
+  if (!packet_ready(v, tag)) {
     const unsigned long long t0 = exch_now_ns();
     unsigned spins = 0;
     do {
@@ -93,9 +96,38 @@ __device__ __forceinline__ bool poll_packet(const ExchangeView& x, const ulonglo
           return false;
         }
       }
-    } while ((v.x & 0xffffffffull) != tag || (v.y & 0xffffffffull) != tag);
+    } while (!packet_ready(v, tag));
   }
   *out = v;
+  return true;
+}
+__device__ __forceinline__ double packet_value(const ulonglong2& v) {
+  return __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
+}
+
+// The packets of every other rank for one element (area(p) + off), summed with `mine` in rank
+// order.  All world-1 loads are issued before any is looked at -- one L2 round trip when the
+// packets have landed, instead of world-1 dependent ones -- and only the late ones are polled.
+__device__ __forceinline__ bool gather_sum(const ExchangeView& x, int64_t area_len, int64_t off, int par,
+                                           unsigned long long tag, double mine, double* out) {
+  ulonglong2 v[kMaxPeers];
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < x.world && p != x.rank) v[p] = ld_packet(x.recv_local + ((int64_t)(p * 2 + par) * area_len + off));
+  double s = 0.0;
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p) {
+    if (p >= x.world) continue;
+    if (p == x.rank) {
+      s += mine;
+      continue;
+    }
+    if (!packet_ready(v[p], tag) &&
+        !poll_packet(x, x.recv_local + ((int64_t)(p * 2 + par) * area_len + off), tag, &v[p]))
+      return false;
+    s += packet_value(v[p]);
+  }
+  *out = s;
   return true;
 }
 
@@ -115,20 +147,9 @@ __device__ __forceinline__ void peer_allreduce_oneshot_body(const ExchangeView& 
     for (int p = 0; p < kMaxPeers; ++p)
       if (p < x.world && p != x.rank)
         st_packet(x.recv_peer[p] + ((int64_t)(x.rank * 2 + par) * len + j), w0, w1);
-    // gather: poll my own areas, sum in rank order
-    double s = 0.0;
-#pragma unroll
-    for (int p = 0; p < kMaxPeers; ++p) {
-      if (p >= x.world) continue;
-      if (p == x.rank) {
-        s += mine;
-        continue;
-      }
-      const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * len + j);
-      ulonglong2 v;
-      if (!poll_packet(x, q, tag, &v)) return;
-      s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
-    }
+    // gather: my own areas, summed in rank order
+    double s;
+    if (!gather_sum(x, len, j, par, tag, mine, &s)) return;
     dst[j] = s;
   }
 }
@@ -166,21 +187,10 @@ __device__ __forceinline__ void peer_allreduce_twoshot_body(const ExchangeView& 
       const ulonglong2* q = x.recv_local + x.gather_off + (int64_t)par * len + j;
       ulonglong2 v;
       if (!poll_packet(x, q, tag, &v)) return;
-      dst[j] = __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
+      dst[j] = packet_value(v);
     } else {
-      double s = 0.0;
-#pragma unroll
-      for (int p = 0; p < kMaxPeers; ++p) {
-        if (p >= x.world) continue;
-        if (p == x.rank) {
-          s += mine;
-          continue;
-        }
-        const ulonglong2* q = x.recv_local + ((int64_t)(p * 2 + par) * x.slice + i);
-        ulonglong2 v;
-        if (!poll_packet(x, q, tag, &v)) return;
-        s += __longlong_as_double((long long)((v.x & 0xffffffff00000000ull) | (v.y >> 32)));
-      }
+      double s;
+      if (!gather_sum(x, x.slice, i, par, tag, mine, &s)) return;
       dst[j] = s;
       const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
       const unsigned long long w0 = ((bits >> 32) << 32) | tag, w1 = ((bits & 0xffffffffull) << 32) | tag;
@@ -209,6 +219,16 @@ struct FusedExchange {
   unsigned int epoch;
   int mode;                        // 0 = off, 1 = one-shot, 2 = two-shot
 };
+
+// The exchange of a sweep kernel's tail, kept out of line: its registers (the batched packet
+// loads) are then allocated on their own and never press on the sweep loop it follows.
+__device__ __noinline__ void fused_exchange_tail(const FusedExchange& fx, const double* src, int64_t len,
+                                                 int64_t first, int64_t stride) {
+  if (fx.mode == 2)
+    peer_allreduce_twoshot_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
+  else
+    peer_allreduce_oneshot_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
+}
 
 class PeerExchange {
  public:

@@ -239,6 +239,11 @@ class DevicePools:
         self._chk(self._lib.cfmm_comm_detach(self._ctx))
         self.peer_attached = False
 
+    def comm_check(self):
+        """After sweep_device* calls: wait for them and raise CFMMError (CFMM_ERR_COMM) if an
+        exchange gave up on a peer (cfmm_comm_check)."""
+        self._chk(self._lib.cfmm_comm_check(self._ctx))
+
     def attach_group(self, group=None, barrier=True):
         """Join the NVLink peer exchange of a torch.distributed group (one
         process per GPU): export this rank's handle, all-gather the handles

@@ -297,6 +297,11 @@ int cfmm_comm_export(cfmm_ctx *ctx, void *handle_out /* CFMM_COMM_HANDLE_BYTES *
 int cfmm_comm_attach(cfmm_ctx *ctx, int world, int rank,
                      const void *handles /* world * CFMM_COMM_HANDLE_BYTES */);
 int cfmm_comm_detach(cfmm_ctx *ctx);
+/* After asynchronous sweeps (cfmm_sweep_device*): waits for the stream of the last sweep and
+ * returns CFMM_ERR_COMM if any exchange so far hit its poll bound (a rank that never launched
+ * the matching sweep, a dead peer); CFMM_OK otherwise and for contexts outside a group.
+ * cfmm_sweep makes the same check itself. */
+int cfmm_comm_check(cfmm_ctx *ctx);
 
 #ifdef __cplusplus
 }
