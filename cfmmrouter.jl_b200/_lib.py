@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfmm_b200.so")
+# CFMM_B200_LIB: development override (A/B runs of two builds of the same ABI on one box)
+LIB_PATH = os.environ.get("CFMM_B200_LIB") or os.path.join(_HERE, "libcfmm_b200.so")
 
 CFMM_OK = 0
 CFMM_ERR_INVALID = -1

@@ -106,15 +106,13 @@ __device__ __forceinline__ double packet_value(const ulonglong2& v) {
 }
 
 // The packets of every other rank for one element (area(p) + off), summed with `mine` in rank
-// order.  All world-1 loads are issued before any is looked at -- one L2 round trip when the
-// packets have landed, instead of world-1 dependent ones -- and only the late ones are polled.
+// order.  First pass: every packet is loaded once, back to back (independent loads: one L2 round
+// trip when all of them have landed, instead of world-1 dependent ones).  Only when one was late:
+// second pass, polling them in turn.
 __device__ __forceinline__ bool gather_sum(const ExchangeView& x, int64_t area_len, int64_t off, int par,
                                            unsigned long long tag, double mine, double* out) {
-  ulonglong2 v[kMaxPeers];
-#pragma unroll
-  for (int p = 0; p < kMaxPeers; ++p)
-    if (p < x.world && p != x.rank) v[p] = ld_packet(x.recv_local + ((int64_t)(p * 2 + par) * area_len + off));
   double s = 0.0;
+  bool all = true;
 #pragma unroll
   for (int p = 0; p < kMaxPeers; ++p) {
     if (p >= x.world) continue;
@@ -122,10 +120,23 @@ __device__ __forceinline__ bool gather_sum(const ExchangeView& x, int64_t area_l
       s += mine;
       continue;
     }
-    if (!packet_ready(v[p], tag) &&
-        !poll_packet(x, x.recv_local + ((int64_t)(p * 2 + par) * area_len + off), tag, &v[p]))
-      return false;
-    s += packet_value(v[p]);
+    const ulonglong2 v = ld_packet(x.recv_local + ((int64_t)(p * 2 + par) * area_len + off));
+    all = all && packet_ready(v, tag);
+    s += packet_value(v);
+  }
+  if (!all) {
+    s = 0.0;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p >= x.world) continue;
+      if (p == x.rank) {
+        s += mine;
+        continue;
+      }
+      ulonglong2 v;
+      if (!poll_packet(x, x.recv_local + ((int64_t)(p * 2 + par) * area_len + off), tag, &v)) return false;
+      s += packet_value(v);
+    }
   }
   *out = s;
   return true;
@@ -220,10 +231,9 @@ struct FusedExchange {
   int mode;                        // 0 = off, 1 = one-shot, 2 = two-shot
 };
 
-// The exchange of a sweep kernel's tail, kept out of line: its registers (the batched packet
-// loads) are then allocated on their own and never press on the sweep loop it follows.
-__device__ __noinline__ void fused_exchange_tail(const FusedExchange& fx, const double* src, int64_t len,
-                                                 int64_t first, int64_t stride) {
+// The exchange in a sweep kernel's tail.
+__device__ __forceinline__ void fused_exchange_tail(const FusedExchange& fx, const double* src, int64_t len,
+                                                    int64_t first, int64_t stride) {
   if (fx.mode == 2)
     peer_allreduce_twoshot_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
   else
