@@ -57,7 +57,9 @@ def parse_args():
     ap.add_argument("--workload", default="config5_10M_product_50k_tokens", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer")
-    ap.add_argument("--two-shot", type=int, default=-1, help="peer exchange protocol: -1 auto (two-shot for N>2), 0, 1")
+    ap.add_argument("--protocol", type=int, default=0,
+                    help="peer exchange protocol: 0 = library default (3, direct 8-byte push), 1 = LL one-shot, "
+                         "2 = LL two-shot")
     ap.add_argument("--nu", choices=["near", "wide", "ones"], default="near")
     ap.add_argument("--exact", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -313,8 +315,8 @@ def run_ours(args):
                 if rank == 0:
                     print(f"[bench] peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
                 exchange = "nccl"
-            if exchange == "peer" and args.two_shot >= 0:
-                pools.set_option("exchange_two_shot", args.two_shot)
+            if exchange == "peer" and args.protocol > 0:
+                pools.set_option("exchange_protocol", args.protocol)
             flag = torch.tensor([1 if exchange == "peer" else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() == 0 and exchange == "peer":
@@ -475,7 +477,9 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kind = WORKLOADS[args.workload][2]
         roofline = roofline_object(prof, prof_times, ms_total, args.steps, launches, kind, m_local,
-                                   alg_bytes, peak, peak_src, args.workload, flushed)
+                                   alg_bytes, peak, peak_src, args.workload, flushed,
+                                   geomean_tma=not any(o.replace(" ", "") in ("geomean_tma=0", "use_tma=0", "geomean_log2=0")
+                                                       for o in args.opt))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -493,6 +497,9 @@ def run_ours(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "pools_per_gpu": m_local, "pools_total": total_pools,
                        "n_tokens": n, "nu": args.nu, "exact_mode": args.exact, "exchange": exchange,
+                       "exchange_protocol": (None if exchange != "peer" else
+                                             {0: "direct 8-byte push (1 hop)", 3: "direct 8-byte push (1 hop)",
+                                              1: "LL one-shot", 2: "LL two-shot"}[args.protocol]),
                        "l2": "inputs larger than L2 (320 MB/GPU > 126 MB)" if alg_bytes > 126e6
                              else ("L2 flushed (256 MB written) before every timed step; the warm figure is in l2_warm"
                                    if flushed else "L2-WARM: working set fits in L2, no flush between steps")},
@@ -621,8 +628,8 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
     ps.finalize()
     ps.set_option("sweep_events", 0)
     ps.attach_group(dist.group.WORLD)
-    if args.two_shot >= 0:
-        ps.set_option("exchange_two_shot", args.two_shot)
+    if args.protocol > 0:
+        ps.set_option("exchange_protocol", args.protocol)
     fn = make_step(ps)
     steps = max(args.steps, 200)
     for _ in range(10):
@@ -653,7 +660,7 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
 
 
 def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, alg_bytes, peak, peak_src,
-                    workload, flushed):
+                    workload, flushed, geomean_tma=True):
     """The `roofline` object of the JSON line, from the event-bracketed launches of timed
     region 2.  prof[t] = (total_ms, launches) and prof_times[t] = per-launch ms for pool type
     t (3 = peer exchange); ms_total / launches belong to timed region 1 (no events between
@@ -661,9 +668,12 @@ def roofline_object(prof, prof_times, ms_total, steps, launches, kind, m_local, 
     # dominant kernel = the one with the most event-timed device time
     dom = max((0, 1, 2), key=lambda t: prof[t][0])
     dom_ms, dom_cnt = prof[dom]
-    dom_name = {0: "product_sweep_tma (ProductTwoCoin gradient sweep)", 1: "sweep_kernel<GeomeanPools>",
+    dom_name = {0: "product_sweep_tma<ProductTwoCoin> (gradient sweep, TMA ring kernel)",
+                1: "product_sweep_tma<GeometricMeanTwoCoin> (gradient sweep, TMA ring kernel, 48-byte records)"
+                   if geomean_tma else "sweep_kernel<GeomeanPools>",
                 2: "sweep_kernel<Univ3Pools>"}[dom]
-    traffic = read_traffic(workload, {0: "product_sweep_tma", 1: "sweep_kernel_geomean", 2: "sweep_kernel_univ3"}[dom])
+    traffic = read_traffic(workload, {0: "product_sweep_tma", 1: "product_sweep_tma_geomean" if geomean_tma
+                                      else "sweep_kernel_geomean", 2: "sweep_kernel_univ3"}[dom])
     if kind == "mixed":
         dom_bytes = (m_local // 2) * (32 if dom == 0 else 48)
     else:

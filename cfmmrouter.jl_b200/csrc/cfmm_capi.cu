@@ -161,6 +161,7 @@ struct cfmm_ctx {
   DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
+  int exchange_protocol = 3;      // 1 = LL one-shot, 2 = LL two-shot, 3 = direct 8-byte push (peer_exchange.cuh)
   int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured: +8 us back to back, +330 us after an event or copy)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
@@ -1784,8 +1785,15 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->coop_launch = value != 0;
   } else if (!strcmp(key, "exchange_bypass")) {
     ctx->exchange_bypass = value != 0;
-  } else if (!strcmp(key, "exchange_two_shot")) {
-    ctx->comm.force_mode((int)value);
+  } else if (!strcmp(key, "exchange_two_shot")) {  // the two LL forms (peer_exchange.cuh)
+    ctx->exchange_protocol = value != 0 ? 2 : 1;
+    ctx->comm.force_mode(ctx->exchange_protocol);
+    ctx->state_version++;
+  } else if (!strcmp(key, "exchange_protocol")) {
+    if (value < 1 || value > 3) return fail(ctx, CFMM_ERR_INVALID, "exchange_protocol: 1, 2 or 3");
+    ctx->exchange_protocol = (int)value;
+    ctx->comm.force_mode(ctx->exchange_protocol);
+    ctx->state_version++;
   } else if (!strcmp(key, "sweep_events")) {
     ctx->sweep_events = value != 0;
   } else if (!strcmp(key, "gradient_math")) {
@@ -1960,6 +1968,7 @@ int cfmm_comm_attach(cfmm_ctx* ctx, int world, int rank, const void* handles) {
   if (!ctx->comm.attach(world, rank, (const unsigned char*)handles,
                         CFMM_COMM_HANDLE_BYTES, ctx->sm_count))
     return fail(ctx, CFMM_ERR_COMM, "comm attach failed: %s", ctx->comm.error().c_str());
+  ctx->comm.force_mode(ctx->exchange_protocol);  // an option set before the attach holds
   return CFMM_OK;
 }
 

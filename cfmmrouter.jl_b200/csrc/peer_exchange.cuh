@@ -65,6 +65,7 @@ struct ExchangeView {
   int world, rank;
   int64_t slice;                      // two-shot: tokens owned per rank = ceil(len / world)
   int64_t gather_off;                 // two-shot: packet offset of the gathered-result area
+  int64_t direct_off;                 // direct protocol: offset (in packets) of its 8-byte areas
   unsigned* error;                    // device word raised when a poll times out (host: CFMM_ERR_COMM)
 };
 
@@ -221,6 +222,80 @@ __global__ void __launch_bounds__(kExchangeThreads)
                               (int64_t)gridDim.x * blockDim.x);
 }
 
+// Direct protocol (default): ONE hop for any world size and 8 bytes per value.  A receive slot
+// holds either the "empty" pattern (all ones: a NaN no arithmetic produces -- hardware NaNs are
+// 0x7ff8000000000000 -- and a partial that carries exactly it is sent as the canonical NaN) or a
+// value: the 8-byte store is atomic, so the value validates itself and needs no tag.  Every rank
+// pushes its partial to all peers (area(src = me, parity)), polls its own world-1 slots with all
+// loads of a pass issued back to back, sums the world values in rank order -- the same values in
+// the same order everywhere: bitwise-identical results -- and resets the slots it consumed.  A
+// slot is written again two exchanges later, which the writer cannot start before this rank
+// has finished the next exchange (it needs this rank's contribution), i.e. after this kernel:
+// the reset is never overtaken.  Per rank (W-1)·len·8 bytes leave over NVLink (2.8 MB at W = 8,
+// n = 50k: ~3 us of wire time) against two dependent hops of the two-shot LL form.
+constexpr unsigned long long kDirectEmpty = ~0ull;
+__device__ __forceinline__ void st_u64_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_allreduce_direct_body(const ExchangeView& x, const double* src, double* dst,
+                                                           int64_t len, unsigned int epoch, int64_t first,
+                                                           int64_t stride) {
+  const int par = (int)(epoch & 1u);
+  unsigned long long* local = reinterpret_cast<unsigned long long*>(x.recv_local + x.direct_off);
+  for (int64_t j = first; j < len; j += stride) {
+    unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(src + j));
+    if (bits == kDirectEmpty) bits = 0x7ff8000000000000ull;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < x.world && p != x.rank)
+        st_u64_sys(reinterpret_cast<unsigned long long*>(x.recv_peer[p] + x.direct_off) +
+                       ((int64_t)(x.rank * 2 + par) * len + j),
+                   bits);
+    double s;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      bool all = true;
+      s = 0.0;
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p >= x.world) continue;
+        unsigned long long v = bits;
+        if (p != x.rank) {
+          v = ld_u64_sys(local + ((int64_t)(p * 2 + par) * len + j));
+          all = all && v != kDirectEmpty;
+        }
+        s += __longlong_as_double((long long)v);
+      }
+      if (all) break;
+      if (spins == 0) t0 = exch_now_ns();
+      if ((++spins & 1023u) == 0u) {
+        if (*reinterpret_cast<volatile unsigned*>(x.error)) return;  // somebody already gave up
+        if (exch_now_ns() - t0 > kPollTimeoutNs) {
+          atomicExch(x.error, 1u);
+          return;
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < x.world && p != x.rank) st_u64_sys(local + ((int64_t)(p * 2 + par) * len + j), kDirectEmpty);
+    dst[j] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kExchangeThreads)
+    peer_allreduce_direct_kernel(ExchangeView x, const double* src, double* dst, int64_t len,
+                                 unsigned int epoch) {
+  peer_allreduce_direct_body(x, src, dst, len, epoch, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                             (int64_t)gridDim.x * blockDim.x);
+}
+
 // What a sweep kernel needs to run the exchange in its own tail.
 struct FusedExchange {
   ExchangeView view;
@@ -228,13 +303,15 @@ struct FusedExchange {
   unsigned long long* grid_done;   // device counter: CTAs that finished accumulating, all sweeps
   unsigned long long target;       // value grid_done reaches when every CTA of THIS sweep is done
   unsigned int epoch;
-  int mode;                        // 0 = off, 1 = one-shot, 2 = two-shot
+  int mode;                        // 0 = off, 1 = LL one-shot, 2 = LL two-shot, 3 = direct
 };
 
 // The exchange in a sweep kernel's tail.
 __device__ __forceinline__ void fused_exchange_tail(const FusedExchange& fx, const double* src, int64_t len,
                                                     int64_t first, int64_t stride) {
-  if (fx.mode == 2)
+  if (fx.mode == 3)
+    peer_allreduce_direct_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
+  else if (fx.mode == 2)
     peer_allreduce_twoshot_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
   else
     peer_allreduce_oneshot_body(fx.view, src, fx.dst, len, fx.epoch, first, stride);
@@ -245,12 +322,14 @@ class PeerExchange {
   bool attached() const { return attached_ && world_ > 1; }
   const std::string& error() const { return err_; }
   int launches_per_reduce() const { return 1; }
-  void force_mode(int two_shot) { two_shot_ = two_shot != 0 && world_ > 1; }
+  // protocol: 1 = LL one-shot, 2 = LL two-shot, 3 = direct (default)
+  void force_mode(int mode) { mode_ = world_ > 1 && mode >= 1 && mode <= 3 ? mode : 3; }
+  int mode() const { return mode_; }
   // fused use: the sweep kernel itself runs the exchange body; returns the epoch to tag with
   unsigned int begin_fused(int* mode) {
     ++epoch_;
     if (epoch_ == 0) epoch_ = 2;
-    *mode = two_shot_ ? 2 : 1;
+    *mode = mode_;
     return epoch_;
   }
   const ExchangeView& view() const { return view_; }
@@ -264,10 +343,14 @@ class PeerExchange {
   bool export_handle(int64_t len, PeerHandle* out) {
     if (!base_) {
       len_ = len;
-      // kMaxPeers contribution areas x 2 parities, plus 2 gathered-result areas (two-shot)
-      bytes_ = (size_t)(kMaxPeers + 1) * 2 * (size_t)len * sizeof(ulonglong2);
+      // LL: kMaxPeers contribution areas x 2 parities, plus 2 gathered-result areas (two-shot);
+      // direct: kMaxPeers x 2 areas of 8-byte slots behind them, all "empty"
+      const size_t ll_bytes = (size_t)(kMaxPeers + 1) * 2 * (size_t)len * sizeof(ulonglong2);
+      const size_t direct_bytes = (size_t)kMaxPeers * 2 * (size_t)len * sizeof(unsigned long long);
+      bytes_ = ll_bytes + direct_bytes;
       if (!ok(cudaMalloc(&base_, bytes_), "cudaMalloc(exchange)")) return false;
-      if (!ok(cudaMemset(base_, 0, bytes_), "cudaMemset(exchange)")) return false;
+      if (!ok(cudaMemset(base_, 0, ll_bytes), "cudaMemset(exchange)")) return false;
+      if (!ok(cudaMemset((char*)base_ + ll_bytes, 0xff, direct_bytes), "cudaMemset(exchange)")) return false;
       if (!ok(cudaMalloc(&err_word_, sizeof(unsigned)), "cudaMalloc(exchange error word)")) return false;
       if (!ok(cudaMemset(err_word_, 0, sizeof(unsigned)), "cudaMemset(exchange error word)")) return false;
     }
@@ -307,8 +390,9 @@ class PeerExchange {
     view_.recv_local = (ulonglong2*)base_;
     view_.slice = (len_ + world - 1) / world;
     view_.gather_off = (int64_t)kMaxPeers * 2 * len_;
+    view_.direct_off = (int64_t)(kMaxPeers + 1) * 2 * len_;
     view_.error = err_word_;
-    two_shot_ = world > 2;
+    mode_ = 3;
     for (int p = 0; p < world; ++p) {
       PeerHandle h;
       memcpy(&h, handles + (size_t)p * stride, sizeof(h));
@@ -352,7 +436,9 @@ class PeerExchange {
     }
     ++epoch_;
     if (epoch_ == 0) epoch_ = 2;  // 0 is the value of untouched memory; keep parity moving
-    if (two_shot_)
+    if (mode_ == 3)
+      peer_allreduce_direct_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
+    else if (mode_ == 2)
       peer_allreduce_twoshot_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
     else
       peer_allreduce_kernel<<<grid_, kExchangeThreads, 0, st>>>(view_, src, dst, len, epoch_);
@@ -387,7 +473,7 @@ class PeerExchange {
   int world_ = 1, rank_ = 0, grid_ = 64;
   unsigned int epoch_ = 0;
   bool attached_ = false;
-  bool two_shot_ = false;
+  int mode_ = 3;
   ExchangeView view_;
   std::string err_;
 };

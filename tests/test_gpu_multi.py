@@ -95,10 +95,16 @@ def test_two_contexts_one_process_peer_exchange(cr, oracle):
     for r, (p, _) in enumerate(pools):
         p._chk(p._lib.cfmm_comm_attach(p._ctx, world, r, handles))
     ref, accref, tol, atol = _reference(oracle)
-    for sweep in range(7):  # several epochs: slot double-buffering; both protocols
-        if sweep == 3:  # switch to the two-shot (reduce-scatter + gather) protocol
+    for sweep in range(11):  # several epochs: slot double-buffering; all three protocols
+        if sweep == 3:  # from the direct push to the LL two-shot (reduce-scatter + gather) protocol
             for p, _ in pools:
                 p.set_option("exchange_two_shot", 1)
+        if sweep == 6:  # LL one-shot
+            for p, _ in pools:
+                p.set_option("exchange_protocol", 1)
+        if sweep == 8:  # and back to the direct push: its slots must have been left empty
+            for p, _ in pools:
+                p.set_option("exchange_protocol", 3)
         out = [None] * world
 
         def run(r):
@@ -128,9 +134,10 @@ def _worker(rank, world, port, out_dir):
     try:
         p, v = _shard(cr, rank, world)
         p.attach_group(dist.group.WORLD)  # cudaIpc handles over torch.distributed
-        res = [p.sweep(v) for _ in range(2)]
-        p.set_option("exchange_two_shot", 1 if world == 2 else 0)  # the protocol that is not the default here
-        res += [p.sweep(v) for _ in range(2)]
+        res = [p.sweep(v) for _ in range(3)]  # direct push (default)
+        for proto in (2, 1, 3):  # LL two-shot, LL one-shot, direct again
+            p.set_option("exchange_protocol", proto)
+            res += [p.sweep(v) for _ in range(2)]
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), psi=np.stack([r[0] for r in res]),
                  acc=np.array([r[1] for r in res]))
         # product-only pool set: fused compute+collective kernel (and, for contrast, the unfused path)
@@ -142,8 +149,9 @@ def _worker(rank, world, port, out_dir):
         q.set_option("fused_exchange", 0)
         fres += [q.sweep(vq) for _ in range(2)]
         q.set_option("fused_exchange", 1)
-        q.set_option("exchange_two_shot", 1 if world == 2 else 0)
-        fres += [q.sweep(vq) for _ in range(2)]
+        for proto in (2, 1, 3):
+            q.set_option("exchange_protocol", proto)
+            fres += [q.sweep(vq) for _ in range(2)]
         q.set_option("coop_launch", 1)  # the same fused kernel under cudaLaunchCooperativeKernel
         fres += [q.sweep(vq) for _ in range(2)]
         q.set_option("coop_launch", 0)
@@ -173,7 +181,7 @@ def test_one_process_per_gpu_ipc_exchange(cr, oracle, tmp_path):
     outs = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     for o in outs[1:]:  # bitwise-identical reduced vectors on every rank
         assert np.array_equal(outs[0]["psi"], o["psi"]) and np.array_equal(outs[0]["acc"], o["acc"])
-    for k in range(4):
+    for k in range(outs[0]["psi"].shape[0]):
         assert np.all(np.abs(outs[0]["psi"][k] - ref) <= tol)
         assert abs(outs[0]["acc"][k] - accref) <= atol
     # fused path: one launch per sweep, same bits on every rank, right answer

@@ -26,6 +26,7 @@ def bind(path):
     lib = C.CDLL(path)
     lib.cfmm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64]
     lib.cfmm_add_product.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _ip]
+    lib.cfmm_add_geomean.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _ip, _dp]
     lib.cfmm_finalize.argtypes = [C.c_void_p]
     lib.cfmm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.cfmm_sweep_device_view.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -37,14 +38,19 @@ def bind(path):
 
 
 class Ctx:
-    def __init__(self, lib, n, R, g, Ai, pre):
+    def __init__(self, lib, n, R, g, Ai, pre, w=None):
         self.lib, self.n = lib, n
+        self.ptype = 0 if w is None else 1
         self.ctx = C.c_void_p()
         assert lib.cfmm_create(C.byref(self.ctx), 0, n) == 0
         for k, v in pre.items():
             self.opt(k, v)
-        assert lib.cfmm_add_product(self.ctx, len(g), R.ctypes.data_as(_dp), g.ctypes.data_as(_dp),
-                                    Ai.ctypes.data_as(_ip)) == 0
+        if w is None:
+            assert lib.cfmm_add_product(self.ctx, len(g), R.ctypes.data_as(_dp), g.ctypes.data_as(_dp),
+                                        Ai.ctypes.data_as(_ip)) == 0
+        else:
+            assert lib.cfmm_add_geomean(self.ctx, len(g), R.ctypes.data_as(_dp), g.ctypes.data_as(_dp),
+                                        Ai.ctypes.data_as(_ip), w.ctypes.data_as(_dp)) == 0
         assert lib.cfmm_finalize(self.ctx) == 0, lib.cfmm_last_error(self.ctx)
 
     def opt(self, k, v):
@@ -59,9 +65,9 @@ class Ctx:
 
     def times(self):
         cnt = C.c_int64()
-        self.lib.cfmm_profile_read_times(self.ctx, 0, None, 0, C.byref(cnt))
+        self.lib.cfmm_profile_read_times(self.ctx, self.ptype, None, 0, C.byref(cnt))
         buf = np.zeros(cnt.value, dtype=np.float32)
-        self.lib.cfmm_profile_read_times(self.ctx, 0, buf.ctypes.data_as(C.POINTER(C.c_float)), cnt.value, C.byref(cnt))
+        self.lib.cfmm_profile_read_times(self.ctx, self.ptype, buf.ctypes.data_as(C.POINTER(C.c_float)), cnt.value, C.byref(cnt))
         return buf.astype(np.float64) * 1e3
 
     def close(self):
@@ -87,10 +93,17 @@ def main():
     ap.add_argument("--pre", default="")
     ap.add_argument("--nu", default="near")
     ap.add_argument("--out", default="")
+    ap.add_argument("--type", default="product", choices=["product", "geomean"])
+    ap.add_argument("--flush", action="store_true", help="write 256 MB (> L2) before every timed launch")
     a = ap.parse_args()
     libs = dict(x.split("=", 1) for x in a.lib) or {"new": os.path.join(ROOT, "cfmmrouter.jl_b200", "libcfmm_b200.so")}
     optsets = a.opt or [""]
-    R, g, Ai = synth.product_pools(a.m, a.n, seed=1234)
+    w = None
+    if a.type == "geomean":
+        R, g, Ai, w = synth.geomean_pools(a.m, a.n)
+    else:
+        R, g, Ai = synth.product_pools(a.m, a.n, seed=1234)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if a.flush else None
     v = synth.dual_prices(a.n, a.nu)
     d_nu = torch.from_numpy(v).cuda()
     st = torch.cuda.current_stream().cuda_stream
@@ -101,7 +114,7 @@ def main():
         for o in optsets:
             kv = dict((x.split("=")[0], int(x.split("=")[1])) for x in o.split(",") if x)
             try:
-                c = Ctx(lib, a.n, R, g, Ai, pre)
+                c = Ctx(lib, a.n, R, g, Ai, pre, w)
                 for k, val in kv.items():
                     c.opt(k, val)
                 c.opt("sweep_events", 0)
@@ -124,6 +137,8 @@ def main():
         for name, c in cfgs:
             c.opt("profile", a.iters)
             for _ in range(a.iters):
+                if flush_buf is not None:
+                    flush_buf.zero_()
                 c.sweep(d_nu, st)
             torch.cuda.synchronize()
             res[name].append(c.times())
@@ -131,7 +146,7 @@ def main():
     out = []
     for name, _ in cfgs:
         t = np.concatenate(res[name])
-        row = {"cfg": name, "m": a.m, "n": a.n, "median_us": float(np.median(t)), "mean_us": float(t.mean()),
+        row = {"cfg": name, "type": a.type, "flushed": bool(a.flush), "m": a.m, "n": a.n, "median_us": float(np.median(t)), "mean_us": float(t.mean()),
                "min_us": float(t.min()), "p95_us": float(np.quantile(t, 0.95)), "launches": len(t)}
         print(json.dumps(row), flush=True)
         out.append(row)
