@@ -257,10 +257,47 @@ __device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w
 // so a visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
 constexpr int kTickStride = 16;
 
-// find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395.  Both walk directions
-// share one loop (the direction is data: index step and record half), so a
-// warp whose lanes walk in different directions does not execute two loops.
-__device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks,
+// The tick a walk STARTS in (the current tick) is additionally stored per pool, in pool order,
+// as four coalesced double2 streams (Univ3First): (k, R_1+α), (R_2+β, current_price),
+// (δmax↑, R_2), (δmax↓, R_1) -- 64 bytes per pool, every byte of which a trading pool uses.
+// ncu on the CSR-only form: 170 MB of DRAM reads against 48 MB algorithmic on config 4,
+// because one touched 32-byte sector of a 128-byte tick costs a 128-byte fetch, behind a
+// dependent load (tick_off -> record).  Most walks end in the tick they start in: they now read
+// pool-indexed streams only, and the CSR is touched by the walks that cross a boundary.
+struct Univ3First {
+  double k, ra, rb;          // loaded with the pool header
+  const double2* up;         // (δmax↑, R_2) of this pool
+  const double2* dn;         // (δmax↓, R_1)
+};
+
+// find_arb_pos (src/cfmms.jl:321-337) on one precomputed (flipped, :289) tick: sub = t.R_1 + t.α,
+// load_b() = (δ_max, t.R_2), load_rb() = t.R_2 + t.β.  Returns false when the walk stops (:362, :384).
+template <class LoadB, class LoadRb>
+__device__ __forceinline__ bool univ3_tick(double k, double sub, double price, bool initial, LoadB load_b,
+                                           LoadRb load_rb, double& dsum, double& lsum) {
+  double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), sub), l;
+  if (d <= 0.0) {
+    d = 0.0;
+    l = 0.0;
+  } else {
+    const double2 b = load_b();
+    if (d >= b.x) {
+      d = b.x;
+      l = b.y;
+    } else {
+      l = __dsub_rn(load_rb(), __dsqrt_rn(__dmul_rn(price, k)));
+    }
+  }
+  if (!initial && (d == 0.0 || l == 0.0)) return false;
+  dsum = __dadd_rn(dsum, d);
+  lsum = __dadd_rn(lsum, l);
+  return true;
+}
+
+// find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395.  Both walk directions share one loop (the
+// direction is data: index step and record half), so a warp whose lanes walk in different
+// directions does not execute two loops.  The first visited tick comes from the per-pool record.
+__device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks, const Univ3First& first,
                                            double current_price, int current_tick, double g,
                                            double v1, double v2) {
   Trade t;
@@ -275,35 +312,25 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const int step = up ? 1 : -1;
   const int last = up ? n_ticks : 1;
   const double* rec0 = td + (up ? 0 : 8);
-  bool initial = true;
   double dsum = 0.0, lsum = 0.0;
-  for (int idx = current_tick; up ? (idx <= last) : (idx >= last); idx += step) {
+  int idx = current_tick;
+  if (up ? (idx <= last) : (idx >= last)) {
+    // is_empty_pool (k == 0): skipped, not terminal (:354-357, :376-379)
+    if (first.k != 0.0)
+      univ3_tick(
+          first.k, up ? first.ra : first.rb, price, true, [&]() { return __ldg(up ? first.up : first.dn); },
+          [&]() { return up ? first.rb : first.ra; }, dsum, lsum);
+    idx += step;
+  }
+  for (; up ? (idx <= last) : (idx >= last); idx += step) {
     const double2* tk = reinterpret_cast<const double2*>(rec0 + (size_t)(idx - 1) * kTickStride);
     const double2 a = __ldg(tk);  // (k, t.R_1 + t.α) of the (flipped) tick
-    const double k = a.x;
-    if (k == 0.0) {  // is_empty_pool: skipped, not terminal (:354-357, :376-379)
-      initial = false;
-      continue;
-    }
-    // find_arb_pos (src/cfmms.jl:321-337) on the (flipped, :289) precomputed tick
-    double d = __dsub_rn(__dsqrt_rn(__ddiv_rn(k, price)), a.y), l;
-    if (d <= 0.0) {
-      d = 0.0;
-      l = 0.0;
-    } else {
-      const double2 b = __ldg(tk + 1);  // (δ_max, t.R_2): same 32-byte sector as a
-      if (d >= b.x) {
-        d = b.x;
-        l = b.y;
-      } else {
-        const double rb = __ldg(reinterpret_cast<const double*>(tk + 2));  // t.R_2 + t.β (second sector)
-        l = __dsub_rn(rb, __dsqrt_rn(__dmul_rn(price, k)));
-      }
-    }
-    if (!initial && (d == 0.0 || l == 0.0)) break;  // :362, :384
-    dsum = __dadd_rn(dsum, d);
-    lsum = __dadd_rn(lsum, l);
-    initial = false;
+    if (a.x == 0.0) continue;
+    if (!univ3_tick(
+            a.x, a.y, price, false, [&]() { return __ldg(tk + 1); },  // (δ_max, t.R_2): same 32-byte sector as a
+            [&]() { return __ldg(reinterpret_cast<const double*>(tk + 2)); },  // t.R_2 + t.β (second sector)
+            dsum, lsum))
+      break;
   }
   const double dn = __ddiv_rn(dsum, g);  // pre-fee tendered amount :371, :391
   if (up) {

@@ -74,7 +74,8 @@ struct PoolSet {
   cfmm::HVec<int64_t> order;              // sorted position -> insertion index within type
   std::vector<int64_t> pos_of;            // lazily: insertion index -> sorted position
   DevBuf<double2> d_R, d_w, d_outD, d_outL;
-  DevBuf<double> d_gam, d_cp, d_tickdata;
+  DevBuf<double> d_gam, d_tickdata;
+  DevBuf<double2> d_first[4];             // univ3: the current tick of every pool, four streams (arb_math.cuh)
   DevBuf<int2> d_Ai, d_tick;
   DevBuf<int64_t> d_gidx;                 // sorted position -> global insertion index
   int64_t total_ticks = 0;
@@ -113,7 +114,8 @@ struct PoolSet {
   bool skewed = false;          // product: hub tokens detected at finalize
   void release() {
     d_R.release(); d_w.release(); d_outD.release(); d_outL.release();
-    d_gam.release(); d_cp.release(); d_tickdata.release();
+    d_gam.release(); d_tickdata.release();
+    for (auto& f : d_first) f.release();
     d_Ai.release(); d_tick.release(); d_gidx.release();
     d_packed.release(); d_inv_scale.release(); d_tok_sum.release(); d_gcode.release(); d_gtab.release();
     if (h_dur) cudaFreeHost(h_dur);
@@ -475,7 +477,9 @@ int upload_set(cfmm_ctx* ctx, int type) {
   if (type == CFMM_POOL_UNIV3) {
     // compute_at_tick (src/cfmms.jl:294-313) for every tick, once, on the host:
     // IEEE sqrt / div / mul / sub in the reference's order (see arb_math.cuh)
-    std::vector<double> cp((size_t)m), td;
+    std::vector<double> td;
+    std::vector<double2> first[4];
+    for (auto& f : first) f.assign((size_t)m, make_double2(0.0, 0.0));
     std::vector<int2> tick((size_t)m);
     td.reserve(s.lower.size() * cfmm::kTickStride);
     int64_t n_ticks_total = 0;
@@ -483,7 +487,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
       const int64_t i = s.order[(size_t)p];
       const int64_t b = s.tick_off[(size_t)i], e = s.tick_off[(size_t)i + 1];
       const double price = s.cp[(size_t)i];
-      cp[(size_t)p] = price;
+      first[1][(size_t)p].y = price;
       // current_tick = searchsortedlast(lower_ticks, current_price; rev=true)
       // (src/cfmms.jl:235): number of leading ticks >= current_price
       int cur = 0;
@@ -507,11 +511,17 @@ int upload_set(cfmm_ctx* ctx, int type) {
         const double rec[cfmm::kTickStride] = {k, ra, dmax_up, R2, rb, 0.0, 0.0, 0.0,
                                                k, rb, dmax_dn, R1, ra, 0.0, 0.0, 0.0};
         td.insert(td.end(), rec, rec + cfmm::kTickStride);
+        if (idx == cur) {  // the tick a walk starts in: also per pool, in pool order
+          first[0][(size_t)p] = make_double2(k, ra);
+          first[1][(size_t)p].x = rb;
+          first[2][(size_t)p] = make_double2(dmax_up, R2);
+          first[3][(size_t)p] = make_double2(dmax_dn, R1);
+        }
       }
       n_ticks_total += e - b;
     }
     s.total_ticks = n_ticks_total;
-    CU_TRY(ctx, s.d_cp.upload(cp));
+    for (int f = 0; f < 4; ++f) CU_TRY(ctx, s.d_first[f].upload(first[f]));
     CU_TRY(ctx, s.d_tick.upload(tick));
     CU_TRY(ctx, s.d_tickdata.upload(td));
   }
@@ -898,7 +908,7 @@ int enqueue_sweep(cfmm_ctx* ctx, const double* d_v, double* d_dst, bool mat,
     PoolSet& s = ctx->sets[CFMM_POOL_UNIV3];
     constexpr int PT = CFMM_POOL_UNIV3;
     if (s.m > 0) {
-      cfmm::Univ3Pools p{s.d_cp.p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
+      cfmm::Univ3Pools p{s.d_first[0].p, s.d_first[1].p, s.d_first[2].p, s.d_first[3].p, s.d_gam.p, s.d_Ai.p, s.d_tick.p,
                          s.d_tickdata.p, s.m_padded, (int)s.total_ticks};
       if ((rc = launch_sweep(ctx, PT, p, s, d_v, d_psi, mat, st)) != CFMM_OK) return rc;
     }

@@ -139,20 +139,30 @@ struct GeomeanPoolsLog2 : GeomeanPools {
 };
 
 struct Univ3Pools {
-  const double* cp;       // current_price
+  const double2* f0;      // (k, R_1+α) of the current tick, per pool   \  the tick a walk starts in
+  const double2* f1;      // (R_2+β, current_price)                      |  (arb_math.cuh, Univ3First):
+  const double2* f2;      // (δmax↑, R_2)                                |  64 B per pool, pool order
+  const double2* f3;      // (δmax↓, R_1)                               /
   const double* gam;
   const int2* Ai;
-  const int2* tick;       // (tick_off, current_tick 1-based)   -> 32 B header
+  const int2* tick;       // (tick_off, current_tick 1-based)
   const double* tickdata; // CSR, kTickStride doubles per tick (precomputed BoundedProduct, see arb_math.cuh)
   int64_t m;
   int total_ticks;
   struct Pool {
     double cp, g;
     int off, cur, nt;
+    Univ3First first;
   };
   __device__ __forceinline__ Pool load(int64_t i) const {
     Pool p;
-    p.cp = ld_stream(cp + i);
+    const double2 a = ld_stream(f0 + i), b = ld_stream(f1 + i);
+    p.first.k = a.x;
+    p.first.ra = a.y;
+    p.first.rb = b.x;
+    p.first.up = f2 + i;
+    p.first.dn = f3 + i;
+    p.cp = b.y;
     p.g = ld_stream(gam + i);
     const int2 t = ld_stream(tick + i);
     p.off = t.x;
@@ -163,7 +173,7 @@ struct Univ3Pools {
   }
   __device__ __forceinline__ Trade arb(const Pool& p, double v1, double v2,
                                        bool, bool) const {
-    return univ3_arb(tickdata + (size_t)p.off * kTickStride, p.nt, p.cp, p.cur, p.g, v1, v2);
+    return univ3_arb(tickdata + (size_t)p.off * kTickStride, p.nt, p.first, p.cp, p.cur, p.g, v1, v2);
   }
 };
 
