@@ -347,6 +347,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler_ref = [None]
+    host_enqueue_us = [0.0]
 
     def timed_region(steps, fn=None, flush=False):
         """ms of `steps` steps on the stream (CUDA events, barrier + synchronize on both sides).
@@ -368,8 +369,10 @@ def run_ours(args):
             return float(sum(a.elapsed_time(b) for a, b in ev))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        th0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_enqueue_us[0] = 1e6 * (time.perf_counter() - th0) / max(steps, 1)  # host time to ENQUEUE a step
         e1.record(stream)
         if sampler_ref[0] is not None:
             sampler_ref[0]._sample_once()  # GPU still busy with the queued steps
@@ -389,6 +392,7 @@ def run_ours(args):
         sampler.start()
         ms_total = timed_region(args.steps, flush=flushed)
         launches = pools.launch_count - l0
+        extra["host_enqueue_us_per_step"] = host_enqueue_us[0]
         # a driver-sized K can be a millisecond of GPU time: also a region of >= 50 ms of the
         # same steps (`sustained`), so that the clocks are sampled under load
         ms_dec = ms_total
@@ -435,7 +439,7 @@ def run_ours(args):
         # ---- per-phase timeline of the fused sweep+exchange kernel on rank 0 (%globaltimer stamps of
         # every CTA; measurement option "trace", outside the timed regions) ---------------------
         if world > 1 and exchange == "peer" and WORKLOADS[args.workload][2] == "product":
-            extra["phases_rank0_us"] = phase_trace(pools, step, barrier, rank)
+            extra["phases_rank0_us"] = phase_trace(pools, step, barrier, rank, dist=dist, world=world)
         # ---- N > 1, outside every timed region: is the reduced [Ψ; acc] right? --------------
         if world > 1 and args.verify and exchange == "peer":
             extra["parity_checked"], extra["parity"] = verify_reduction(
@@ -446,7 +450,7 @@ def run_ours(args):
         if world > 1 and args.scaling == "weak" and args.strong and exchange == "peer" \
                 and WORKLOADS[args.workload][2] == "product":
             extra["strong"] = strong_scaling_run(torch, dist, cr, args, pools, make_step, timed_region, barrier,
-                                                 rank, world, local_rank, dev)
+                                                 rank, world, local_rank, dev, host_enqueue_us)
 
     # max over ranks
     if world > 1:
@@ -527,7 +531,7 @@ def _view(torch, ptr, count, dev):
     return torch.as_tensor(h, device=dev)
 
 
-def phase_trace(pools, step, barrier, rank):
+def phase_trace(pools, step, barrier, rank, dist=None, world=1):
     """Median over 8 sweeps of the kernel's phases on this rank, from the per-CTA %globaltimer stamps:
     chunk loop done (slowest CTA), partials flushed, grid barrier passed, exit (exchange done)."""
     pools.set_option("trace", 1)
@@ -551,9 +555,18 @@ def phase_trace(pools, step, barrier, rank):
                      "grid_barrier_passed_med": float(np.median(rel(6))) if t[:, 6].any() else None,
                      "exit_max": float(rel(5).max())})
     pools.set_option("trace", 0)
-    if not rows or rank != 0:
-        return None
-    return {k: (float(np.median([r[k] for r in rows])) if rows[0][k] is not None else None) for k in rows[0]}
+    mine = None
+    if rows:
+        mine = {k: (float(np.median([r[k] for r in rows])) if rows[0][k] is not None else None) for k in rows[0]}
+    if dist is not None and world > 1:
+        # every rank's own timeline (each relative to its own first CTA): who waits for whom
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        if mine is not None:
+            mine["by_rank"] = [None if r is None else {"flushed_max": r["flushed_max"],
+                                                        "grid_barrier_passed_med": r["grid_barrier_passed_med"],
+                                                        "exit_max": r["exit_max"]} for r in allr]
+    return mine if rank == 0 else None
 
 
 def verify_reduction(torch, dist, pools, shard, nu_host, d_nu, sptr, n, dev, rank, world):
@@ -614,7 +627,7 @@ def verify_reduction(torch, dist, pools, shard, nu_host, d_nu, sptr, n, dev, ran
 
 
 def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_region, barrier, rank, world,
-                       local_rank, dev):
+                       local_rank, dev, host_enqueue_us=None):
     """The workload's pool count split over the ranks (strong scaling), timed like `value`, plus
     the single-GPU time of the same pools (rank 0's weak shard IS that pool set, swept with the
     exchange bypassed) so that the line carries its own speed-up."""
@@ -635,10 +648,20 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
     for _ in range(10):
         fn()
     ms = timed_region(steps, fn)
+    host_us = host_enqueue_us[0] if host_enqueue_us is not None else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    phases = phase_trace(ps, fn, barrier, rank)  # per-phase timeline of the strong step on rank 0
+    phases = phase_trace(ps, fn, barrier, rank, dist=dist, world=world)  # per-phase timeline of the strong step
+    # the same shards without the exchange (and without its grid barrier): kernel + launch per rank
+    ps.set_option("exchange_bypass", 1)
+    for _ in range(5):
+        fn()
+    msb = timed_region(steps, fn)
+    ps.set_option("exchange_bypass", 0)
+    tb = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(tb, torch.tensor([1e3 * msb / steps], dtype=torch.float64, device=dev))
+    bypass_us = [float(x.item()) for x in tb]
     # single GPU, same 10M pools: every rank sweeps its weak shard without the exchange; rank 0's is seed 1234
     pools_weak.set_option("exchange_bypass", 1)
     fn1 = make_step(pools_weak)
@@ -646,15 +669,18 @@ def strong_scaling_run(torch, dist, cr, args, pools_weak, make_step, timed_regio
         fn1()
     ms1 = timed_region(steps, fn1)
     pools_weak.set_option("exchange_bypass", 0)
-    t1 = torch.tensor([ms1 if rank == 0 else 0.0], dtype=torch.float64, device=dev)
-    dist.all_reduce(t1, op=dist.ReduceOp.MAX)
-    ms1 = t1.item()
+    t1 = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(t1, torch.tensor([ms1], dtype=torch.float64, device=dev))
+    weak_alone_us = [1e3 * float(x.item()) / steps for x in t1]  # GPU-to-GPU spread of the same kernel
+    ms1 = float(t1[0].item())
     barrier()
     ps.close()
     return {"pools_total": m, "pools_per_gpu": hi - lo, "steps": steps, "us_per_step": 1e3 * ms / steps,
             "value": m * steps / (ms * 1e-3), "unit": UNIT,
             "single_gpu_us_per_step": 1e3 * ms1 / steps, "speedup_vs_single_gpu": ms1 / ms,
-            "phases_rank0_us": phases,
+            "phases_rank0_us": phases, "host_enqueue_us_per_step": host_us,
+            "no_exchange_us_per_step_by_rank": bypass_us,
+            "weak_shard_alone_us_per_step_by_rank": weak_alone_us,
             "note": "same total pools split over the ranks (BASELINE configs[4] as written); single_gpu = "
                     "rank 0 sweeping all of them alone, in the same run"}
 
