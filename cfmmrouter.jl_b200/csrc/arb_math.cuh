@@ -314,7 +314,21 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const double* rec0 = td + (up ? 0 : 8);
   double dsum = 0.0, lsum = 0.0;
   int idx = current_tick;
-  if (up ? (idx <= last) : (idx >= last)) {
+  const auto in_range = [&](int i) { return up ? (i <= last) : (i >= last); };
+  const auto record = [&](int i) { return reinterpret_cast<const double2*>(rec0 + (size_t)(i - 1) * kTickStride); };
+  // The walk is a chain of dependent record loads (tick i+1 is only visited once tick i is fully
+  // consumed): the NEXT tick's first sector is requested before this tick's sqrt / div chain
+  // starts, so its latency overlaps the arithmetic (ncu: 60 % of the stall samples sat on these
+  // loads).  A prefetched record that is never visited costs one 32-byte sector.
+  double2 a_next = make_double2(0.0, 0.0), b_next = a_next;
+  const auto prefetch = [&](int i) {
+    if (in_range(i)) {
+      a_next = __ldg(record(i));      // (k, t.R_1 + t.α) of the (flipped) tick
+      b_next = __ldg(record(i) + 1);  // (δ_max, t.R_2): same 32-byte sector
+    }
+  };
+  if (in_range(idx)) {
+    prefetch(idx + step);
     // is_empty_pool (k == 0): skipped, not terminal (:354-357, :376-379)
     if (first.k != 0.0)
       univ3_tick(
@@ -322,12 +336,13 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
           [&]() { return up ? first.rb : first.ra; }, dsum, lsum);
     idx += step;
   }
-  for (; up ? (idx <= last) : (idx >= last); idx += step) {
-    const double2* tk = reinterpret_cast<const double2*>(rec0 + (size_t)(idx - 1) * kTickStride);
-    const double2 a = __ldg(tk);  // (k, t.R_1 + t.α) of the (flipped) tick
+  for (; in_range(idx); idx += step) {
+    const double2 a = a_next, b = b_next;
+    const double2* tk = record(idx);
+    prefetch(idx + step);
     if (a.x == 0.0) continue;
     if (!univ3_tick(
-            a.x, a.y, price, false, [&]() { return __ldg(tk + 1); },  // (δ_max, t.R_2): same 32-byte sector as a
+            a.x, a.y, price, false, [&]() { return b; },
             [&]() { return __ldg(reinterpret_cast<const double*>(tk + 2)); },  // t.R_2 + t.β (second sector)
             dsum, lsum))
       break;

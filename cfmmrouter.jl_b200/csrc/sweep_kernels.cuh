@@ -139,6 +139,7 @@ struct GeomeanPoolsLog2 : GeomeanPools {
 };
 
 struct Univ3Pools {
+  static constexpr int kMinBlocks = 3;  // latency-bound walks: 24 warps per SM (<= 85 registers)
   const double2* f0;      // (k, R_1+α) of the current tick, per pool   \  the tick a walk starts in
   const double2* f1;      // (R_2+β, current_price)                      |  (arb_math.cuh, Univ3First):
   const double2* f2;      // (δmax↑, R_2)                                |  64 B per pool, pool order
@@ -181,8 +182,18 @@ struct Univ3Pools {
 
 constexpr int kSweepThreads = 256;
 
+// resident CTAs per SM the register allocation must allow (P::kMinBlocks where a type asks for it)
+template <class P, class = void>
+struct MinBlocks {
+  static constexpr int value = 1;
+};
+template <class P>
+struct MinBlocks<P, decltype((void)P::kMinBlocks)> {
+  static constexpr int value = P::kMinBlocks;
+};
+
 template <class P, bool MAT, int U>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, MinBlocks<P>::value)
     sweep_kernel(P pools, const double* __restrict__ nu, double* __restrict__ psi,
                  int n_tokens, double2* __restrict__ outD,
                  double2* __restrict__ outL, int64_t m, int flags,
