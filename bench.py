@@ -58,8 +58,8 @@ def parse_args():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer")
     ap.add_argument("--protocol", type=int, default=0,
-                    help="peer exchange protocol: 0 = library default (3, direct 8-byte push), 1 = LL one-shot, "
-                         "2 = LL two-shot")
+                    help="peer exchange protocol: 0 = library default (direct 8-byte push up to 4 ranks, LL "
+                         "two-shot beyond), 1 = LL one-shot, 2 = LL two-shot, 3 = direct")
     ap.add_argument("--nu", choices=["near", "wide", "ones"], default="near")
     ap.add_argument("--exact", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -502,7 +502,8 @@ def run_ours(args):
             "config": {"workload": args.workload, "pools_per_gpu": m_local, "pools_total": total_pools,
                        "n_tokens": n, "nu": args.nu, "exact_mode": args.exact, "exchange": exchange,
                        "exchange_protocol": (None if exchange != "peer" else
-                                             {0: "direct 8-byte push (1 hop)", 3: "direct 8-byte push (1 hop)",
+                                             {0: "direct 8-byte push (1 hop)" if world <= 4 else "LL two-shot",
+                                              3: "direct 8-byte push (1 hop)",
                                               1: "LL one-shot", 2: "LL two-shot"}[args.protocol]),
                        "l2": "inputs larger than L2 (320 MB/GPU > 126 MB)" if alg_bytes > 126e6
                              else ("L2 flushed (256 MB written) before every timed step; the warm figure is in l2_warm"

@@ -164,7 +164,7 @@ struct cfmm_ctx {
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
   int grid_waves = -1;            // first-generation kernel: CTAs per resident slot (-1: per type, see launch_sweep)
-  int exchange_protocol = 3;      // 1 = LL one-shot, 2 = LL two-shot, 3 = direct 8-byte push (peer_exchange.cuh)
+  int exchange_protocol = 0;      // 0 = by world size, 1 = LL one-shot, 2 = LL two-shot, 3 = direct 8-byte push (peer_exchange.cuh)
   int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured: +8 us back to back, +330 us after an event or copy)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
@@ -1809,7 +1809,7 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     ctx->comm.force_mode(ctx->exchange_protocol);
     ctx->state_version++;
   } else if (!strcmp(key, "exchange_protocol")) {
-    if (value < 1 || value > 3) return fail(ctx, CFMM_ERR_INVALID, "exchange_protocol: 1, 2 or 3");
+    if (value < 0 || value > 3) return fail(ctx, CFMM_ERR_INVALID, "exchange_protocol: 0 (auto), 1, 2 or 3");
     ctx->exchange_protocol = (int)value;
     ctx->comm.force_mode(ctx->exchange_protocol);
     ctx->state_version++;

@@ -322,8 +322,11 @@ class PeerExchange {
   bool attached() const { return attached_ && world_ > 1; }
   const std::string& error() const { return err_; }
   int launches_per_reduce() const { return 1; }
-  // protocol: 1 = LL one-shot, 2 = LL two-shot, 3 = direct (default)
-  void force_mode(int mode) { mode_ = world_ > 1 && mode >= 1 && mode <= 3 ? mode : 3; }
+  // protocol: 1 = LL one-shot, 2 = LL two-shot, 3 = direct; anything else = by world size: the
+  // direct push up to 4 ranks, LL two-shot beyond (measured on B200 / NVSwitch, 10M pools per GPU,
+  // us per step: N=2 60.6 / 61.5 (LL1) / 62.3 (LL2); N=4 63.1 / - / 64.3; N=8 68.9 / 74.9 / 66.1 --
+  // the bytes a rank sends cost ~2.5 us per MB here, more than the second hop beyond 4 ranks)
+  void force_mode(int mode) { mode_ = mode >= 1 && mode <= 3 ? mode : (world_ <= 4 ? 3 : 2); }
   int mode() const { return mode_; }
   // fused use: the sweep kernel itself runs the exchange body; returns the epoch to tag with
   unsigned int begin_fused(int* mode) {
@@ -392,7 +395,7 @@ class PeerExchange {
     view_.gather_off = (int64_t)kMaxPeers * 2 * len_;
     view_.direct_off = (int64_t)(kMaxPeers + 1) * 2 * len_;
     view_.error = err_word_;
-    mode_ = 3;
+    force_mode(0);
     for (int p = 0; p < world; ++p) {
       PeerHandle h;
       memcpy(&h, handles + (size_t)p * stride, sizeof(h));

@@ -225,11 +225,12 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *                      record or a copy precedes it on the stream.
  *   "exchange_bypass"  multi-GPU: 1 = sweeps skip the exchange and return this rank's partial
  *                      [psi ; acc] (verification; every rank must set it alike).
- *   "exchange_protocol" multi-GPU: how [psi ; acc] is summed over NVLink peer memory: 3 (default)
- *                      = direct push, one hop, 8 bytes per value (a receive slot is "empty" or a
- *                      value); 1 = LL one-shot (16-byte epoch-tagged packets, one hop); 2 = LL
- *                      two-shot (reduce-scatter + all-gather, two hops, fewest bytes).  Every
- *                      rank of the group must use the same one.
+ *   "exchange_protocol" multi-GPU: how [psi ; acc] is summed over NVLink peer memory: 3 = direct
+ *                      push, one hop, 8 bytes per value (a receive slot is "empty" or a value);
+ *                      1 = LL one-shot (16-byte epoch-tagged packets, one hop); 2 = LL two-shot
+ *                      (reduce-scatter + all-gather, two hops, fewest bytes); 0 (default) = by
+ *                      group size: 3 up to 4 ranks, 2 beyond.  Every rank of the group must use
+ *                      the same one.
  *   "exchange_two_shot" multi-GPU: 0 / 1 = "exchange_protocol" 1 / 2.
  *   "sweep_events"     1 = record the two CUDA events cfmm_last_sweep_ms needs around every
  *                      sweep (default 0; turns the sweep graphs off).
