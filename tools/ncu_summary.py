@@ -26,10 +26,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"]
 
 
-def raw(rep):
+def raw(rep, match=""):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, first = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    kn = hdr.index("Kernel Name")
+    first = next((r for r in rows[2:] if match in r[kn]), rows[2])  # first launch whose name contains `match`
     d = {}
     for h, u, v in zip(hdr, units, first):
         if h in KEYS or h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
@@ -67,10 +69,13 @@ if __name__ == "__main__":
     ap.add_argument("rep")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--json", default="")
+    ap.add_argument("--match", default="", help="summarise the first launch whose kernel name contains this")
+    ap.add_argument("--no-source", action="store_true")
     a = ap.parse_args()
-    d = raw(a.rep)
+    d = raw(a.rep, a.match)
     print(json.dumps(d, indent=1))
     if a.json:
         with open(a.json, "w") as f:
             json.dump(d, f, indent=1)
-    source(a.rep, a.top)
+    if not a.no_source:
+        source(a.rep, a.top)
