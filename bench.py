@@ -380,10 +380,35 @@ def run_ours(args):
         pools.comm_check()  # a timed-out exchange must fail the run, not slow it
         return e0.elapsed_time(e1)
 
+    def spin_up(min_ms=20.0):
+        """Untimed sweeps until the GPU has been busy for min_ms: after an idle period (setup, a
+        host-side pause between regions) the first ~20 launches run 2-4 us slower than the steady
+        state (tools/ramp_probe.py: 59.9 -> 57.8 -> 55.9 us over launches 0-5 / 5-20 / 20+); a short
+        synchronize does not bring that back.  Called right before every timed region's barrier."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        done = 0
+        while True:
+            for _ in range(64):
+                step()
+            done += 64
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:  # every rank must run the same number of sweeps: they exchange
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ms = t.item()
+            if ms >= min_ms or done >= 50_000:
+                return done
+
     extra = {}
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup)):
             step()
+        extra["spin_up"] = {"min_ms": 20.0, "steps": spin_up(),
+                            "note": "untimed sweeps after the W warm-up steps and before each timed region, until "
+                                    "the GPU has been busy 20 ms (clock / launch pipeline ramp after idle)"}
         barrier()
         # ---- timed region 1: K steps, nothing but the sweeps on the stream -> `value`
         l0 = pools.launch_count
@@ -412,6 +437,7 @@ def run_ours(args):
         # ---- timed region 2: the same K steps with a CUDA-event pair around every
         # kernel launch (on the launching stream) -> per-kernel durations for `roofline`
         n_kernels = 2 if args.workload.startswith("config3") else 1
+        spin_up()
         pools.set_option("profile", args.steps * (n_kernels + (1 if exchange == "peer" else 0)))
         timed_region(args.steps, flush=flushed)
         prof = {t: pools.profile_read(t) for t in (0, 1, 2, 3)}

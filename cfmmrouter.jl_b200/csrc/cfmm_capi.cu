@@ -163,7 +163,7 @@ struct cfmm_ctx {
   DevBuf<unsigned long long> d_grid_done;  // fused exchange: CTAs arrived, summed over all sweeps
   unsigned long long grid_done_target = 0;
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
-  int grid_waves = -1;            // first-generation kernel: CTAs per resident slot (-1: per type, see launch_sweep)
+  int grid_waves = -1;            // first-generation kernel: waves of CTAs (-1 = 1; 0 = one CTA per 512 pools; see launch_sweep)
   int exchange_protocol = 0;      // 0 = by world size, 1 = LL one-shot, 2 = LL two-shot, 3 = direct 8-byte push (peer_exchange.cuh)
   int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured: +8 us back to back, +330 us after an event or copy)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
@@ -604,11 +604,10 @@ int launch_sweep(cfmm_ctx* ctx, int ptype, const P& pools, PoolSet& s,
     if (occ < 1) occ = 1;
   }
   const int per_sm = ctx->blocks_per_sm > 0 && ctx->blocks_per_sm < occ ? ctx->blocks_per_sm : occ;
-  // grid_waves: 1 = one wave of resident CTAs striding over the pools (streaming types: equal work
-  // per pool); 0 = one CTA per 512 pools, handed out by the hardware block scheduler as CTAs
-  // retire (UniV3: the tick walks make the work per pool uneven, and a strided grid pays for the
-  // slowest stride plus the quantisation of its last partial wave)
-  const int waves = ctx->grid_waves >= 0 ? ctx->grid_waves : (ptype == CFMM_POOL_UNIV3 ? 0 : 1);
+  // grid_waves: 1 (default) = one wave of resident CTAs striding over the pools; 0 = one CTA per
+  // 512 pools, handed out by the hardware block scheduler (measured on UniV3, whose tick walks
+  // make the work per pool uneven: 47.0 us against 45.2 us for the strided wave -- kept as a knob)
+  const int waves = ctx->grid_waves >= 0 ? ctx->grid_waves : 1;
   const int64_t cap = (int64_t)ctx->sm_count * per_sm * (waves > 0 ? waves : 1);
   if (waves > 0 && blocks > cap) blocks = cap;
   if (mat && s.d_outD.n != (size_t)m_all) {

@@ -209,10 +209,9 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *                      1 always; before cfmm_finalize.
  *   "use_tma"          0 = run the first-generation kernel on the same layout.
  *   "blocks_per_sm"    resident CTAs per SM of the persistent kernels (measurement knob).
- *   "grid_waves"       sweep_kernel (UniV3, materialising sweeps): -1 (default) = per type, 1 = one
- *                      wave of resident CTAs striding over the pools, 0 = one CTA per 512 pools
- *                      (hardware block scheduling; the UniV3 default: uneven work per pool), N =
- *                      N waves (measurement knob).
+ *   "grid_waves"       sweep_kernel (UniV3, materialising sweeps): 1 (default) = one wave of
+ *                      resident CTAs striding over the pools, 0 = one CTA per 512 pools (hardware
+ *                      block scheduling), N = N waves (measurement knob).
  *   "fused_exchange"   multi-GPU: 1 (default) = product-only sweeps run the peer exchange
  *                      in the sweep kernel's tail; 0 = separate exchange launch.
  *   "coop_launch"      multi-GPU: 1 = the fused sweep+exchange kernel is launched with
