@@ -245,17 +245,18 @@ __device__ __forceinline__ Trade geomean_arb_econ(double R1, double R2, double w
 // Every tick's BoundedProduct (src/cfmms.jl:272-278, built by compute_at_tick
 // :294-313) depends only on pool state (liquidity, tick prices, current price),
 // never on ν.  It is therefore evaluated ONCE at cfmm_finalize, on the host,
-// with the same IEEE operations in the same order, and stored per tick as two
-// direction records of 64 bytes each, ordered so that a walk reads ONE 32-byte
-// sector per fully consumed tick and the second sector only for the tick it
-// stops in (round 1 stored one 64-byte record whose two sectors were both needed
-// for every visited tick: ncu showed 2.33x the algorithmic DRAM traffic):
-//   "upper" walk (towards lower prices), doubles 0..7 of the tick:
-//     [k, R_1+α, δmax↑ = k/β − (R_1+α), R_2 | R_2+β, 0, 0, 0]
-//   "lower" walk (the flipped pool, :289), doubles 8..15:
-//     [k, R_2+β, δmax↓ = k/α − (R_2+β), R_1 | R_1+α, 0, 0, 0]
-// so a visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
-constexpr int kTickStride = 16;
+// with the same IEEE operations in the same order, and stored per pool as two
+// DIRECTION BLOCKS of one 32-byte record per tick (kTickStride doubles per tick in all):
+//   "upper" walk (towards lower prices), block 0, tick i:  [k, R_1+α, δmax↑ = k/β − (R_1+α), R_2]
+//   "lower" walk (the flipped pool, :289), block 1, tick i: [k, R_2+β, δmax↓ = k/α − (R_2+β), R_1]
+// A walk reads consecutive 32-byte records of ONE block -- four ticks per 128-byte line, so the
+// dependent loads of a walk mostly hit the line its first record brought in -- and the one extra
+// value the tick it STOPS in needs (R_2+β for the upper walk, R_1+α for the lower) is the second
+// double of the same tick's record in the OTHER block.  (Round 1: one 64-byte record per tick,
+// both sectors needed per visit, 2.33x the algorithmic DRAM traffic; first form of round 2: 128
+// bytes per tick, one touched sector per 128-byte line.)
+// A visited tick costs find_arb_pos only (2 sqrt + 2 div), bit-identically.
+constexpr int kTickStride = 8;
 
 // The tick a walk STARTS in (the current tick) is additionally stored per pool, in pool order,
 // as four coalesced double2 streams (Univ3First): (k, R_1+α), (R_2+β, current_price),
@@ -297,6 +298,7 @@ __device__ __forceinline__ bool univ3_tick(double k, double sub, double price, b
 // find_arb!(Δ, Λ, ::UniV3, v), src/cfmms.jl:339-395.  Both walk directions share one loop (the
 // direction is data: index step and record half), so a warp whose lanes walk in different
 // directions does not execute two loops.  The first visited tick comes from the per-pool record.
+// td: this pool's two direction blocks (n_ticks records of 4 doubles each, upper then lower).
 __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_ticks, const Univ3First& first,
                                            double current_price, int current_tick, double g,
                                            double v1, double v2) {
@@ -311,11 +313,12 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const double price = __ddiv_rn(up ? p : 1.0, up ? g : __dmul_rn(g, p));
   const int step = up ? 1 : -1;
   const int last = up ? n_ticks : 1;
-  const double* rec0 = td + (up ? 0 : 8);
+  const double* rec0 = td + (up ? 0 : 4 * n_ticks);   // this walk's block
+  const double* other = td + (up ? 4 * n_ticks : 0);  // the other block: (R_2+β | R_1+α) at [1]
   double dsum = 0.0, lsum = 0.0;
   int idx = current_tick;
   const auto in_range = [&](int i) { return up ? (i <= last) : (i >= last); };
-  const auto record = [&](int i) { return reinterpret_cast<const double2*>(rec0 + (size_t)(i - 1) * kTickStride); };
+  const auto record = [&](int i) { return reinterpret_cast<const double2*>(rec0 + (size_t)(i - 1) * 4); };
   // The walk is a chain of dependent record loads (tick i+1 is only visited once tick i is fully
   // consumed): the NEXT tick's first sector is requested before this tick's sqrt / div chain
   // starts, so its latency overlaps the arithmetic (ncu: 60 % of the stall samples sat on these
@@ -338,12 +341,11 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   }
   for (; in_range(idx); idx += step) {
     const double2 a = a_next, b = b_next;
-    const double2* tk = record(idx);
     prefetch(idx + step);
     if (a.x == 0.0) continue;
     if (!univ3_tick(
             a.x, a.y, price, false, [&]() { return b; },
-            [&]() { return __ldg(reinterpret_cast<const double*>(tk + 2)); },  // t.R_2 + t.β (second sector)
+            [&]() { return __ldg(other + (size_t)(idx - 1) * 4 + 1); },  // t.R_2 + t.β: the other block's record
             dsum, lsum))
       break;
   }

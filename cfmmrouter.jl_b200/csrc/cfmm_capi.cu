@@ -165,7 +165,7 @@ struct cfmm_ctx {
   int fused_exchange = 1;         // product-only sets: run the peer exchange in the sweep kernel's tail
   int grid_waves = -1;            // first-generation kernel: waves of CTAs (-1 = 1; 0 = one CTA per 512 pools; see launch_sweep)
   int exchange_protocol = 0;      // 0 = by world size, 1 = LL one-shot, 2 = LL two-shot, 3 = direct 8-byte push (peer_exchange.cuh)
-  int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured: +8 us back to back, +330 us after an event or copy)
+  int coop_launch = 0;            // fused exchange: launch the sweep kernel cooperatively (measured at N = 2: +4 to +8 us per step)
   int exchange_bypass = 0;        // 1 = sweeps return this rank's partial [Ψ; acc] (no exchange); every rank must agree
   cfmm::FusedExchange fx_pending; // set by enqueue_sweep when the next TMA launch must carry the exchange
   int blocks_per_sm = 0;  // 0 = occupancy-derived
@@ -482,7 +482,7 @@ int upload_set(cfmm_ctx* ctx, int type) {
     std::vector<double2> first[4];
     for (auto& f : first) f.assign((size_t)m, make_double2(0.0, 0.0));
     std::vector<int2> tick((size_t)m);
-    td.reserve(s.lower.size() * cfmm::kTickStride);
+    td.assign(s.lower.size() * cfmm::kTickStride, 0.0);
     int64_t n_ticks_total = 0;
     for (int64_t p = 0; p < m; ++p) {
       const int64_t i = s.order[(size_t)p];
@@ -508,10 +508,13 @@ int upload_set(cfmm_ctx* ctx, int type) {
         volatile double rb = R2 + beta;
         volatile double dmax_up = k / beta - ra;
         volatile double dmax_dn = k / alpha - rb;
-        // two direction records of one 32-byte sector + spill each (arb_math.cuh)
-        const double rec[cfmm::kTickStride] = {k, ra, dmax_up, R2, rb, 0.0, 0.0, 0.0,
-                                               k, rb, dmax_dn, R1, ra, 0.0, 0.0, 0.0};
-        td.insert(td.end(), rec, rec + cfmm::kTickStride);
+        // two direction blocks per pool, one 32-byte record per tick in each (arb_math.cuh)
+        const size_t base = (size_t)n_ticks_total * cfmm::kTickStride, nt = (size_t)(e - b), ti = (size_t)(q - b);
+        const double up_rec[4] = {k, ra, dmax_up, R2}, dn_rec[4] = {k, rb, dmax_dn, R1};
+        for (int c = 0; c < 4; ++c) {
+          td[base + ti * 4 + c] = up_rec[c];
+          td[base + nt * 4 + ti * 4 + c] = dn_rec[c];
+        }
         if (idx == cur) {  // the tick a walk starts in: also per pool, in pool order
           first[0][(size_t)p] = make_double2(k, ra);
           first[1][(size_t)p].x = rb;

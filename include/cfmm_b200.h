@@ -220,8 +220,7 @@ int cfmm_solve(cfmm_ctx *ctx, const double *lin, const double *lower, const doub
  *                      residency follows from the occupancy query that sizes the persistent grid,
  *                      and a barrier that cannot complete ends in CFMM_ERR_COMM after the poll
  *                      bound instead of hanging.  Measured at N = 2 on B200: the cooperative
- *                      launch costs +8 us per step back to back and +330 us whenever an event
- *                      record or a copy precedes it on the stream.
+ *                      launch costs +4 to +8 us per step.
  *   "exchange_bypass"  multi-GPU: 1 = sweeps skip the exchange and return this rank's partial
  *                      [psi ; acc] (verification; every rank must set it alike).
  *   "exchange_protocol" multi-GPU: how [psi ; acc] is summed over NVLink peer memory: 3 = direct

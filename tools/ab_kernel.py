@@ -104,6 +104,7 @@ def main():
     else:
         R, g, Ai = synth.product_pools(a.m, a.n, seed=1234)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if a.flush else None
+    flush_rd = torch.zeros(32 << 20, dtype=torch.int64, device="cuda") if a.flush else None  # read pass: no dirty lines left
     v = synth.dual_prices(a.n, a.nu)
     d_nu = torch.from_numpy(v).cuda()
     st = torch.cuda.current_stream().cuda_stream
@@ -139,6 +140,7 @@ def main():
             for _ in range(a.iters):
                 if flush_buf is not None:
                     flush_buf.zero_()
+                    flush_rd.sum()
                 c.sweep(d_nu, st)
             torch.cuda.synchronize()
             res[name].append(c.times())
