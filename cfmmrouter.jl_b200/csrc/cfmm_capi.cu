@@ -51,7 +51,16 @@ struct DevBuf {
   cudaError_t upload(const std::vector<T>& h) {
     cudaError_t e = alloc(h.size());
     if (e != cudaSuccess || h.empty()) return e;
-    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return copy_in(p, h.data(), h.size() * sizeof(T));
+  }
+  // H2D from pageable memory, COMPLETE on return.  cudaMemcpy alone is not: for pageable sources
+  // it returns once the data sits in the driver's staging buffer, the DMA may still be in flight --
+  // and the contexts' streams are non-blocking, so a kernel launched on them right afterwards does
+  // not wait for the legacy stream the copy ran on (seen as a rare illegal address in
+  // update_reserves_kernel reading a position array that had not landed yet).
+  static cudaError_t copy_in(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e;
   }
   void release() {
     if (p) cudaFree(p);
@@ -1216,7 +1225,7 @@ int cfmm_finalize(cfmm_ctx* ctx) {
     for (int t : {CFMM_POOL_PRODUCT, CFMM_POOL_GEOMEAN}) any = any || (ctx->sets[t].m > 0 && ctx->sets[t].tma_ok);
     if (any && ctx->balance) {
       std::vector<double> ones((size_t)ctx->n_tokens, 1.0);
-      CU_TRY(ctx, cudaMemcpy(ctx->d_nu.p, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CU_TRY(ctx, DevBuf<double>::copy_in(ctx->d_nu.p, ones.data(), ones.size() * sizeof(double)));
       ctx->calibrating = true;
       int rc = CFMM_OK;
       for (int it = 0; it < 12 && rc == CFMM_OK; ++it) {
@@ -1702,8 +1711,7 @@ int cfmm_update_reserves(cfmm_ctx* ctx, int type, int64_t first, int64_t count,
   CU_TRY(ctx, d_new.upload(newR));
   cudaError_t e = d_pos.alloc((size_t)count);
   if (e == cudaSuccess)
-    e = cudaMemcpy(d_pos.p, s.pos_of.data() + first, (size_t)count * sizeof(int64_t),
-                   cudaMemcpyHostToDevice);
+    e = DevBuf<int64_t>::copy_in(d_pos.p, s.pos_of.data() + first, (size_t)count * sizeof(int64_t));
   if (e == cudaSuccess) {
     const int threads = 256;
     cfmm::update_reserves_kernel<<<(unsigned)((count + threads - 1) / threads), threads, 0,
