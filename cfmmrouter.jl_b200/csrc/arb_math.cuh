@@ -320,36 +320,28 @@ __device__ __forceinline__ Trade univ3_arb(const double* __restrict__ td, int n_
   const auto in_range = [&](int i) { return up ? (i <= last) : (i >= last); };
   const auto record = [&](int i) { return reinterpret_cast<const double2*>(rec0 + (size_t)(i - 1) * 4); };
   // The walk is a chain of dependent record loads (tick i+1 is only visited once tick i is fully
-  // consumed): the NEXT tick's record is requested before this tick's sqrt / div chain starts, so
-  // its latency overlaps the arithmetic (ncu: 60 % of the stall samples sat on these loads).  From
-  // the first tick the request is only made when a two-multiply estimate says the tick will be
-  // consumed (k >= price·(R+α+δmax)², i.e. δ >= δmax up to rounding): a walk that ends where it
-  // starts -- most of them -- never touches the CSR.  The estimate only steers the prefetch; a
-  // record that was not requested is loaded when the walk gets there.
+  // consumed): the NEXT tick's first sector is requested before this tick's sqrt / div chain
+  // starts, so its latency overlaps the arithmetic (ncu: 60 % of the stall samples sat on these
+  // loads).  A prefetched record that is never visited costs one 32-byte sector.
   double2 a_next = make_double2(0.0, 0.0), b_next = a_next;
-  bool have_next = false;
   const auto prefetch = [&](int i) {
-    have_next = in_range(i);
-    if (have_next) {
+    if (in_range(i)) {
       a_next = __ldg(record(i));      // (k, t.R_1 + t.α) of the (flipped) tick
-      b_next = __ldg(record(i) + 1);  // (δ_max, t.R_2)
+      b_next = __ldg(record(i) + 1);  // (δ_max, t.R_2): same 32-byte sector
     }
   };
   if (in_range(idx)) {
-    const double sub = up ? first.ra : first.rb;
-    const double2 hb = __ldg(up ? first.up : first.dn);  // (δ_max, t.R_2) of the current tick
-    const double full = sub + hb.x;
-    if (first.k == 0.0 || first.k >= price * full * full * 0.999999) prefetch(idx + step);
+    prefetch(idx + step);
     // is_empty_pool (k == 0): skipped, not terminal (:354-357, :376-379)
     if (first.k != 0.0)
       univ3_tick(
-          first.k, sub, price, true, [&]() { return hb; }, [&]() { return up ? first.rb : first.ra; }, dsum, lsum);
+          first.k, up ? first.ra : first.rb, price, true, [&]() { return __ldg(up ? first.up : first.dn); },
+          [&]() { return up ? first.rb : first.ra; }, dsum, lsum);
     idx += step;
   }
   for (; in_range(idx); idx += step) {
-    if (!have_next) prefetch(idx);
     const double2 a = a_next, b = b_next;
-    prefetch(idx + step);  // (same 128-byte line as this record, three times out of four)
+    prefetch(idx + step);
     if (a.x == 0.0) continue;
     if (!univ3_tick(
             a.x, a.y, price, false, [&]() { return b; },
