@@ -52,7 +52,11 @@ def test_roofline_object_mixed_and_exchange():
     assert r["kernel"].startswith("product_sweep_tma<GeometricMeanTwoCoin>")
     assert r["algorithmic_bytes_per_launch"] == 500_000 * 48
     assert "back_to_back" not in r          # several launches per step: no single-kernel figure
-    assert abs(r["exchange_avg_us"] - 12.0) < 1e-9 and r["traffic"] is None
+    assert abs(r["exchange_avg_us"] - 12.0) < 1e-9
+    assert r["traffic"] == bench.read_traffic("config3_1M_mixed_10k_tokens", "product_sweep_tma_geomean")
+    r2 = bench.roofline_object(prof, pt, 45.0, 100, 300, "mixed", 1_000_000, 40e6, 6650.0, "fallback",
+                               "some_other_workload", True)
+    assert r2["traffic"] is None            # no capture of that workload: no number
 
 
 def test_reference_arm_prints_contract_line():
