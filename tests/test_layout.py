@@ -76,6 +76,26 @@ def test_uniform_graph_layout(cr, m, n, variant):
         assert lay["nb"] == -(-n // B) and lay["nb"] <= 1600
 
 
+@pytest.mark.parametrize("m,n,variant", [(300_000, 12_000, 0), (300_000, 1_500, 0), (200_000, 3_200, 0),
+                                         (300_000, 12_000, -1)])
+def test_large_sets_take_the_threaded_paths(cr, m, n, variant):
+    """Above 65 536 pools the layout runs its OpenMP forms (threaded counting sort on the bucket
+    keys, buckets sorted concurrently when there are >= 4 of them, the threaded sort inside a
+    bucket otherwise): the order must be exactly the stable (bucket(b), a, insertion index) order."""
+    from cfmmrouter_b200 import synth
+    _, _, Ai = synth.product_pools(m, n, seed=m + n)
+    lay = layout(cr, n, Ai, variant=variant)
+    check_invariants(Ai, n, lay)
+    a, b = Ai[:, 0] - 1, Ai[:, 1] - 1
+    real = lay["order"][lay["order"] >= 0]
+    if variant == -1:
+        assert not lay["bucketed"]
+        assert np.array_equal(real, np.argsort(a, kind="stable"))
+    else:
+        assert lay["bucketed"]
+        assert np.array_equal(real, np.lexsort((np.arange(m), a, b // lay["nb"])))
+
+
 def test_sparse_buckets_fall_back_to_a_sorted(cr):
     from cfmmrouter_b200 import synth
     _, _, Ai = synth.product_pools(3000, 200_000, seed=1)  # 63+ buckets, ~50 pools each
