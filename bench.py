@@ -539,7 +539,7 @@ def run_ours(args):
                                              {0: "direct 8-byte push (1 hop)" if world <= 4 else "LL two-shot",
                                               3: "direct 8-byte push (1 hop)",
                                               1: "LL one-shot", 2: "LL two-shot"}[args.protocol]),
-                       "l2": "inputs larger than L2 (320 MB/GPU > 126 MB)" if alg_bytes > 126e6
+                       "l2": "inputs larger than L2 (320 MB algorithmic, 240-320 MB streamed per launch per GPU > 126 MB)" if alg_bytes > 126e6
                              else ("L2 flushed (256 MB written, then 256 MB read so that no dirty lines remain) before every timed step; the warm figure is in l2_warm"
                                    if flushed else "L2-WARM: working set fits in L2, no flush between steps")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n,

@@ -65,6 +65,7 @@ class DevicePools:
     def __init__(self, n_tokens: int, device: int = 0):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
+        self._ptr_args = {}
         rc = self._lib.cfmm_create(C.byref(self._ctx), int(device), int(n_tokens))
         if rc != _lib.CFMM_OK:
             msg = self._lib.cfmm_last_error(None)
@@ -149,10 +150,15 @@ class DevicePools:
 
     def sweep_into(self, v_ptr: int, psi_ptr: int, acc_ptr: int, materialize: bool = False):
         """Raw-pointer form of sweep (host pointers, e.g. pinned buffers)."""
-        self._chk(self._lib.cfmm_sweep(self._ctx, C.cast(v_ptr, C.POINTER(C.c_double)),
-                                       C.cast(psi_ptr, C.POINTER(C.c_double)),
-                                       C.cast(acc_ptr, C.POINTER(C.c_double)),
-                                       1 if materialize else 0))
+        key = (v_ptr, psi_ptr, acc_ptr)
+        args = self._ptr_args.get(key)
+        if args is None:  # ctypes casts cost microseconds each: keep them for buffers that come back every sweep
+            if len(self._ptr_args) > 64:
+                self._ptr_args.clear()
+            args = self._ptr_args[key] = tuple(C.cast(q, C.POINTER(C.c_double)) for q in key)
+        rc = self._lib.cfmm_sweep(self._ctx, args[0], args[1], args[2], 1 if materialize else 0)
+        if rc != 0:
+            self._chk(rc)
 
     def sweep_device(self, d_v_ptr: int, d_psi_acc_ptr: int, materialize: bool = False,
                      stream_ptr: int = 0):
