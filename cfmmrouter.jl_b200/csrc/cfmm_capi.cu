@@ -744,6 +744,7 @@ int launch_tma_cfg(cfmm_ctx* ctx, PoolSet& s, const double* d_v, double* d_psi, 
       memset(s.h_dur, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned));
       CU_TRY(ctx, s.d_dur.alloc(cfmm::kTmaMaxRanges + 1));
       CU_TRY(ctx, cudaMemset(s.d_dur.p, 0, (cfmm::kTmaMaxRanges + 1) * sizeof(unsigned)));
+      CU_TRY(ctx, cudaStreamSynchronize(cudaStreamLegacy));  // (memsets run on the legacy stream; ours do not wait for it)
       CU_TRY(ctx, cudaEventCreateWithFlags(&s.ev_dur, cudaEventDisableTiming));
     }
     d_dur = s.d_dur.p;
@@ -1017,6 +1018,7 @@ int cfmm_create(cfmm_ctx** out, int device, int64_t n_tokens) {
     CREATE_TRY(a.alloc((size_t)n_tokens + 1));
     CREATE_TRY(cudaMemset(a.p, 0, ((size_t)n_tokens + 1) * sizeof(double)));
   }
+  CREATE_TRY(cudaStreamSynchronize(cudaStreamLegacy));  // the memsets above ran on the legacy stream; ctx->stream does not wait for it
   CREATE_TRY(cudaMallocHost((void**)&ctx->h_stage, (size_t)(n_tokens + 1) * sizeof(double)));
 #undef CREATE_TRY
   *out = ctx;
@@ -1801,6 +1803,7 @@ int cfmm_set_option(cfmm_ctx* ctx, const char* key, int64_t value) {
     if (value) {
       CU_TRY(ctx, ctx->d_trace.alloc((size_t)8 * 4096));
       CU_TRY(ctx, cudaMemset(ctx->d_trace.p, 0, 8 * 4096 * sizeof(unsigned long long)));
+      CU_TRY(ctx, cudaStreamSynchronize(cudaStreamLegacy));
     } else {
       cudaStreamSynchronize(ctx->stream);
       ctx->d_trace.release();

@@ -356,6 +356,9 @@ class PeerExchange {
       if (!ok(cudaMemset((char*)base_ + ll_bytes, 0xff, direct_bytes), "cudaMemset(exchange)")) return false;
       if (!ok(cudaMalloc(&err_word_, sizeof(unsigned)), "cudaMalloc(exchange error word)")) return false;
       if (!ok(cudaMemset(err_word_, 0, sizeof(unsigned)), "cudaMemset(exchange error word)")) return false;
+      // the receive areas must hold their initial pattern before any peer or local kernel looks at
+      // them: memsets run on the legacy stream, which non-blocking streams do not wait for
+      if (!ok(cudaStreamSynchronize(cudaStreamLegacy), "cudaStreamSynchronize(exchange init)")) return false;
     }
     memset(out, 0, sizeof(*out));
     if (!ok(cudaIpcGetMemHandle(&out->ipc, base_), "cudaIpcGetMemHandle")) return false;
